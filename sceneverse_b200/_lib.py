@@ -1,0 +1,69 @@
+"""ctypes binding of libsvpointops (include/svpointops.h).  No fallback: if the CUDA library is
+missing or a call fails this raises — the product path never routes around the native code."""
+import ctypes
+import os
+
+_LIBDIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib")
+_cache = {}
+
+c_int, c_float, c_void_p = ctypes.c_int, ctypes.c_float, ctypes.c_void_p
+
+_POINTOPS_SIGS = {
+    # name: argtypes
+    "sv_fps_f32": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
+    "sv_gather_points_f32": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "sv_gather_points_grad_f32": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "sv_ball_query_f32": [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p],
+    "sv_group_points_f32": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "sv_group_points_grad_f32": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "sv_three_nn_f32": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
+    "sv_three_interpolate_f32": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "sv_three_interpolate_grad_f32": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "sv_fps_ballquery_f32": [c_void_p, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
+}
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+def _load(name):
+    if name in _cache:
+        return _cache[name]
+    path = os.path.join(_LIBDIR, name)
+    if not os.path.exists(path):
+        raise NativeLibraryError(
+            f"{path} is missing: build it with `python -m sceneverse_b200.build` "
+            "(sceneverse_b200 has no CPU or PyTorch fallback)")
+    lib = ctypes.CDLL(path)
+    _cache[name] = lib
+    return lib
+
+
+def pointops():
+    lib = _load("libsvpointops.so")
+    if not getattr(lib, "_sv_ready", False):
+        for fn, argtypes in _POINTOPS_SIGS.items():
+            f = getattr(lib, fn)
+            f.argtypes = argtypes
+            f.restype = c_int
+        lib.sv_version.restype = c_int
+        lib.sv_status_string.restype = ctypes.c_char_p
+        lib.sv_status_string.argtypes = [c_int]
+        lib.sv_last_cuda_error.restype = c_int
+        lib.sv_last_cuda_error_string.restype = ctypes.c_char_p
+        lib.sv_launch_count.restype = ctypes.c_ulonglong
+        lib._sv_ready = True
+    return lib
+
+
+def check(lib, status, what):
+    if status != 0:
+        msg = lib.sv_status_string(status).decode()
+        if status == 2:
+            msg += ": " + lib.sv_last_cuda_error_string().decode()
+        raise RuntimeError(f"{what} failed: {msg}")
+
+
+def launch_count():
+    return int(pointops().sv_launch_count())
