@@ -88,7 +88,7 @@ def make_clouds(seed, n_clouds):
     return np.ascontiguousarray(synthetic.object_batch(seed, n_clouds, PTS, pad_fraction=0.3)[:, :, :3])
 
 
-def cpu_reference_arm(steps, warmup, sample_clouds=256):
+def cpu_reference_arm(steps, warmup, sample_clouds=SCENES * OBJS):
     """Times the CPU oracle (all host threads, OpenMP over clouds) on a bounded sample."""
     from oracle import pointops_ref as R
     R.build()
@@ -157,7 +157,7 @@ def main():
     stream = torch.cuda.current_stream()
 
     def step_resident(i):
-        return _ext.fps_ballquery(dev_in[i % NBUF], NPOINT, RADIUS, NSAMPLE)
+        return _ext.fps_ballquery(dev_in[i % NBUF], NPOINT, RADIUS, NSAMPLE)  # -> sv_sa_sample_f32
 
     h_fi = torch.empty((n_clouds, NPOINT), dtype=torch.int32).pin_memory()
     h_bi = torch.empty((n_clouds, NPOINT, NSAMPLE), dtype=torch.int32).pin_memory()
@@ -212,14 +212,14 @@ def main():
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get("fps_warp_kernel_fused_dram_bytes_per_launch")
+        traffic = json.load(open(tp)).get("sa_sample_kernel_dram_bytes_per_launch")
     out = {
         "metric": "FPS+ball_query Mpts/s (GPS set-abstraction front, model shape)",
         "value": mpts, "unit": "Mpts/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": config,
         "scenes_per_s": world * SCENES / (ms_per_step * 1e-3),
-        "roofline": {"bound": "hbm", "kernel": "fps_warp_kernel<32,fused ball query>", "achieved": achieved,
+        "roofline": {"bound": "hbm", "kernel": "sa_sample_kernel<32> (FPS + ball query, one warp per cloud)", "achieved": achieved,
                      "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": ALG_BYTES_PER_CLOUD * n_clouds,
                      "note": "binding bound is fp32 issue rate, not HBM (DESIGN.md §roofline)"},

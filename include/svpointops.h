@@ -83,6 +83,16 @@ int sv_three_interpolate_grad_f32(const float *grad_out, const int *idx, const f
 int sv_fps_ballquery_f32(const float *xyz, int B, int N, int m, float radius, int nsample,
                          int *fps_idx, float *new_xyz, int *ball_idx, void *stream);
 
+/* Two-level fused sampling for a PointNet++ set-abstraction stack, one pass over xyz (32 <= N <= 1024):
+ * level 1 = sv_fps_ballquery_f32(xyz, m, radius, nsample); level 2 (m2 > 0, requires m == 32) = the
+ * same on the (B,32,3) centres of level 1 with (m2, radius_2, nsample2).  Replaces the reference's
+ * furthest_point_sample + gather_operation + ball_query of two consecutive PointnetSAModules
+ * (pointnet2_modules.py:54-58, pointnet2_utils.py:331); the ball-query distances are taken from the
+ * FPS sweep (bit-identical).  Outputs as in sv_fps_ballquery_f32, per level. */
+int sv_sa_sample_f32(const float *xyz, int B, int N, int m, float radius, int nsample, int *fps_idx,
+                     float *new_xyz, int *ball_idx, int m2, float radius_2, int nsample2, int *fps_idx2,
+                     float *new_xyz2, int *ball_idx2, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,6 +20,8 @@ _POINTOPS_SIGS = {
     "sv_three_interpolate_f32": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "sv_three_interpolate_grad_f32": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "sv_fps_ballquery_f32": [c_void_p, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
+    "sv_sa_sample_f32": [c_void_p, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p, c_void_p,
+                         c_int, c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
 }
 
 
@@ -57,6 +59,27 @@ def pointops():
     return lib
 
 
+_GPS_SIGS = {
+    "sv_tc05_selftest": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
+}
+
+
+def gps():
+    lib = _load("libsvgps.so")
+    if not getattr(lib, "_sv_ready", False):
+        for fn, argtypes in _GPS_SIGS.items():
+            f = getattr(lib, fn)
+            f.argtypes = argtypes
+            f.restype = c_int
+        lib.svgps_launch_count.restype = ctypes.c_ulonglong
+        lib.svgps_last_cuda_error_string.restype = ctypes.c_char_p
+        # status strings live in libsvpointops
+        lib.sv_status_string = pointops().sv_status_string
+        lib.sv_last_cuda_error_string = lib.svgps_last_cuda_error_string
+        lib._sv_ready = True
+    return lib
+
+
 def check(lib, status, what):
     if status != 0:
         msg = lib.sv_status_string(status).decode()
@@ -66,4 +89,9 @@ def check(lib, status, what):
 
 
 def launch_count():
-    return int(pointops().sv_launch_count())
+    """Kernel launches enqueued so far by both native libraries."""
+    n = int(pointops().sv_launch_count())
+    import os as _os
+    if _os.path.exists(_os.path.join(_LIBDIR, "libsvgps.so")):
+        n += int(gps().svgps_launch_count())
+    return n

@@ -19,7 +19,8 @@ NVCC_FLAGS = [
 
 # library name -> sources (relative to csrc/)
 LIBS = {
-    "libsvpointops.so": ["pointops.cu"],
+    "libsvpointops.so": ["pointops.cu", "sa_sample.cu"],
+    "libsvgps.so": ["gps_common.cu", "tc05_selftest.cu"],
 }
 
 

@@ -161,6 +161,43 @@ def fps_ballquery(xyz, npoint, radius, nsample):
     fps_idx = torch.empty((B, npoint), dtype=torch.int32, device=xyz.device)
     new_xyz = torch.empty((B, npoint, 3), dtype=torch.float32, device=xyz.device)
     ball_idx = torch.empty((B, npoint, nsample), dtype=torch.int32, device=xyz.device)
+    if 32 <= N <= 1024:
+        _run("sv_sa_sample_f32", xyz, xyz.data_ptr(), B, N, int(npoint), float(radius), int(nsample),
+             fps_idx.data_ptr(), new_xyz.data_ptr(), ball_idx.data_ptr(), 0, 0.0, 0, None, None, None)
+    else:
+        _run("sv_fps_ballquery_f32", xyz, xyz.data_ptr(), B, N, int(npoint), float(radius), int(nsample),
+             fps_idx.data_ptr(), new_xyz.data_ptr(), ball_idx.data_ptr())
+    return fps_idx, new_xyz, ball_idx
+
+
+def fps_ballquery_scan(xyz, npoint, radius, nsample):
+    """The first-generation fused kernel (FPS, then a lane-per-centre scan); kept for N < 32 and as a
+    cross-check of sa_sample in the tests."""
+    _check(xyz, "xyz", torch.float32)
+    _cuda_only(xyz)
+    B, N, _ = xyz.shape
+    fps_idx = torch.empty((B, npoint), dtype=torch.int32, device=xyz.device)
+    new_xyz = torch.empty((B, npoint, 3), dtype=torch.float32, device=xyz.device)
+    ball_idx = torch.empty((B, npoint, nsample), dtype=torch.int32, device=xyz.device)
     _run("sv_fps_ballquery_f32", xyz, xyz.data_ptr(), B, N, int(npoint), float(radius), int(nsample),
          fps_idx.data_ptr(), new_xyz.data_ptr(), ball_idx.data_ptr())
     return fps_idx, new_xyz, ball_idx
+
+
+def sa_sample2(xyz, npoint, radius, nsample, npoint2, radius2, nsample2):
+    """Two set-abstraction levels of sampling in one launch (sv_sa_sample_f32); npoint must be 32.
+    Returns (fps_idx, new_xyz, ball_idx, fps_idx2, new_xyz2, ball_idx2)."""
+    _check(xyz, "xyz", torch.float32)
+    _cuda_only(xyz)
+    B, N, _ = xyz.shape
+    dev = xyz.device
+    fps_idx = torch.empty((B, npoint), dtype=torch.int32, device=dev)
+    new_xyz = torch.empty((B, npoint, 3), dtype=torch.float32, device=dev)
+    ball_idx = torch.empty((B, npoint, nsample), dtype=torch.int32, device=dev)
+    fps_idx2 = torch.empty((B, npoint2), dtype=torch.int32, device=dev)
+    new_xyz2 = torch.empty((B, npoint2, 3), dtype=torch.float32, device=dev)
+    ball_idx2 = torch.empty((B, npoint2, nsample2), dtype=torch.int32, device=dev)
+    _run("sv_sa_sample_f32", xyz, xyz.data_ptr(), B, N, int(npoint), float(radius), int(nsample),
+         fps_idx.data_ptr(), new_xyz.data_ptr(), ball_idx.data_ptr(), int(npoint2), float(radius2), int(nsample2),
+         fps_idx2.data_ptr(), new_xyz2.data_ptr(), ball_idx2.data_ptr())
+    return fps_idx, new_xyz, ball_idx, fps_idx2, new_xyz2, ball_idx2

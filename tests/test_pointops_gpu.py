@@ -61,6 +61,37 @@ def test_fused_fps_ballquery_equals_separate(ext, oracle, name, radius, nsample)
     np.testing.assert_array_equal(bi.cpu().numpy(), oracle.ball_query(want_x, xyz, radius, nsample))
 
 
+@pytest.mark.parametrize("name", ["sa1_objects", "adversarial_n1024", "ball_n1000", "ball_n1024", "ball_n33", "ball_n513"])
+def test_sa_sample_two_level(ext, oracle, name):
+    """sv_sa_sample_f32: both set-abstraction levels of the GPS object encoder in one launch
+    (npoint 32 -> 16, radius 0.2 -> 0.4, nsample 32; pcd_openvocab_encoder.py:27-32)."""
+    xyz, _ = cases.fps_cases()[name]
+    fi, nx, bi, fi2, nx2, bi2 = ext.sa_sample2(dev(xyz), 32, 0.2, 32, 16, 0.4, 32)
+    w_fi = oracle.furthest_point_sampling(xyz, 32)
+    w_nx = np.take_along_axis(xyz, w_fi[:, :, None].astype(np.int64).repeat(3, 2), 1)
+    np.testing.assert_array_equal(fi.cpu().numpy(), w_fi)
+    np.testing.assert_array_equal(nx.cpu().numpy(), w_nx)
+    np.testing.assert_array_equal(bi.cpu().numpy(), oracle.ball_query(w_nx, xyz, 0.2, 32))
+    w_fi2 = oracle.furthest_point_sampling(w_nx, 16)
+    w_nx2 = np.take_along_axis(w_nx, w_fi2[:, :, None].astype(np.int64).repeat(3, 2), 1)
+    np.testing.assert_array_equal(fi2.cpu().numpy(), w_fi2)
+    np.testing.assert_array_equal(nx2.cpu().numpy(), w_nx2)
+    np.testing.assert_array_equal(bi2.cpu().numpy(), oracle.ball_query(w_nx2, w_nx, 0.4, 32))
+    # the scan-based first-generation kernel must agree too
+    s_fi, s_nx, s_bi = ext.fps_ballquery_scan(dev(xyz), 32, 0.2, 32)
+    assert torch.equal(s_fi, fi) and torch.equal(s_nx, nx) and torch.equal(s_bi, bi)
+
+
+@pytest.mark.parametrize("m,radius,nsample", [(40, 0.3, 7), (70, 0.15, 64), (1, 0.5, 3)])
+def test_sa_sample_general_shapes(ext, oracle, m, radius, nsample):
+    xyz, _ = cases.fps_cases()["ball_n1000"]
+    fi, nx, bi = ext.fps_ballquery(dev(xyz), m, radius, nsample)
+    w_fi = oracle.furthest_point_sampling(xyz, m)
+    w_nx = np.take_along_axis(xyz, w_fi[:, :, None].astype(np.int64).repeat(3, 2), 1)
+    np.testing.assert_array_equal(fi.cpu().numpy(), w_fi)
+    np.testing.assert_array_equal(bi.cpu().numpy(), oracle.ball_query(w_nx, xyz, radius, nsample))
+
+
 def test_group_gather_exact_and_grads(ext, oracle):
     rng = np.random.default_rng(0)
     for (B, C, N, NP, NS) in [(3, 6, 1024, 32, 32), (2, 131, 32, 16, 32), (2, 5, 77, 7, 3), (1, 1, 5, 1, 1)]:
