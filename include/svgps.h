@@ -20,6 +20,22 @@ const char *svgps_last_cuda_error_string(void);
  * one CTA, one TMEM accumulator; mode 0 = the descriptor convention used by the library. */
 int sv_tc05_selftest(const void *A, const void *B, float *D, int N, int K, int mode, void *stream);
 
+/* ---- PointNet++ set-abstraction MLP (inference form: eval-mode BatchNorm folded), tcgen05 ------------------
+ * Replaces QueryAndGroup + SharedMLP(3 x Conv2d1x1+BN+ReLU) + max_pool2d of one PointnetSAModule
+ * (reference: pointnet2_modules.py:34-75, pointnet2_utils.py:314-373, pytorch_utils.py:11-36).
+ * `params` = packed device buffer of sv_sa_mlp_param_bytes(level) bytes built by
+ * sceneverse_b200.modules.pointnet.pack_sa_params: [W1|W2|W3] bf16 in UMMA K-major layout with the BN
+ * scale folded in, then shift1|shift2|shift3 (f32).  Outputs are point-major bf16 (B,npoint,C). */
+int sv_sa_mlp_param_bytes(int level);
+/* level 1: pts (B,P,6) f32 [xyz rgb], new_xyz (B,32,3), ball_idx (B,32,nsample) -> out (B,32,128) bf16
+ * (mlp 6->64->64->128) */
+int sv_sa1_mlp_bf16(const float *pts, const float *new_xyz, const int *ball_idx, const void *params, int B, int P,
+                    int nsample, void *out_feat, void *stream);
+/* level 2: xyz (B,P,3) f32, feat (B,P,128) bf16, new_xyz (B,16,3), ball_idx (B,16,nsample) -> out (B,16,256) bf16
+ * (mlp 131->128->128->256) */
+int sv_sa2_mlp_bf16(const float *xyz, const void *feat, const float *new_xyz, const int *ball_idx, const void *params,
+                    int B, int P, int nsample, void *out_feat, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
