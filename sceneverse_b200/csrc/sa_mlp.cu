@@ -39,7 +39,7 @@ struct SaCfg {
   static constexpr int SHIFT_BYTES = (N1 + N2 + N3) * 4;
   static constexpr int PARAM_BYTES = W1_BYTES + W2_BYTES + W3_BYTES + SHIFT_BYTES;
   static constexpr int TMEM_COLS = (N1 + N2 > N3 ? N1 + N2 : N3) <= 128 ? 128 : 256;
-  static constexpr int SMEM_BYTES = A_BYTES + PARAM_BYTES + 64;
+  static constexpr int SMEM_BYTES = 2 * A_BYTES + PARAM_BYTES + 64;  // two tiles in flight
 };
 
 struct SaMlpArgs {
@@ -70,19 +70,27 @@ __device__ __forceinline__ void epilogue_to_smem(uint32_t taddr, const float *__
   }
 }
 
+// 16-byte async copy global -> shared (LDGSTS); src_bytes = 0 zero-fills
+__device__ __forceinline__ void cp_async16(void *dst, const void *src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// Two tiles (sample slots s and s+1 of the same 128 centres) are in flight per CTA, each with its own
+// A buffer, TMEM column range and mbarrier, so the tensor pipe works on one while the CUDA cores run the
+// epilogue / gather of the other.
 template <class Cfg, int LEVEL>
 __global__ void __launch_bounds__(256, LEVEL == 1 ? 2 : 1) sa_mlp_kernel(const SaMlpArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t *sA = smem;
-  uint8_t *sW1 = smem + Cfg::A_BYTES;
+  uint8_t *sW1 = smem + 2 * Cfg::A_BYTES;
   uint8_t *sW2 = sW1 + Cfg::W1_BYTES;
   uint8_t *sW3 = sW2 + Cfg::W2_BYTES;
   const float *sh1 = reinterpret_cast<const float *>(sW3 + Cfg::W3_BYTES);
   const float *sh2 = sh1 + Cfg::N1;
   const float *sh3 = sh2 + Cfg::N2;
-  uint64_t *wbar = reinterpret_cast<uint64_t *>(smem + Cfg::A_BYTES + Cfg::PARAM_BYTES);
-  uint64_t *mbar = wbar + 1;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(mbar + 1);
+  uint64_t *wbar = reinterpret_cast<uint64_t *>(smem + 2 * Cfg::A_BYTES + Cfg::PARAM_BYTES);
+  uint64_t *mbar = wbar + 1;  // [2]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(mbar + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, wg = tid >> 7;
   const int r = tid & 127;  // row of the tile == TMEM lane == centre within the super-tile
@@ -90,28 +98,65 @@ __global__ void __launch_bounds__(256, LEVEL == 1 ? 2 : 1) sa_mlp_kernel(const S
   if (tid == 0) {
     mbar_init(wbar, 1);
     mbar_init(mbar, 1);
+    mbar_init(mbar + 1, 1);
     mbar_fence_init();
     mbar_expect_tx(wbar, Cfg::PARAM_BYTES);
     bulk_g2s(sW1, a.params, Cfg::PARAM_BYTES, wbar);
   }
-  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
-  // zero the A tile once: padding columns of layer 1 stay zero for the whole kernel
-  for (int e = tid; e < Cfg::K1P * 128 * 2 / 16; e += 256) reinterpret_cast<uint4 *>(sA)[e] = make_uint4(0, 0, 0, 0);
+  if (warp == 1) tmem_alloc<2 * Cfg::TMEM_COLS>(tmem_slot);
+  // zero both A tiles once: K-padding columns that no gather / epilogue writes stay zero for the whole kernel
+  for (int e = tid; e < 2 * Cfg::A_BYTES / 16; e += 256) reinterpret_cast<uint4 *>(smem)[e] = make_uint4(0, 0, 0, 0);
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);  // this warp's 32 TMEM lanes
+  const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;  // this warp's 32 TMEM lanes
   mbar_wait(wbar, 0);
 
   constexpr uint32_t IDESC1 = make_idesc_bf16(128, Cfg::N1), IDESC2 = make_idesc_bf16(128, Cfg::N2),
                      IDESC3 = make_idesc_bf16(128, Cfg::N3);
-  constexpr uint32_t COL1 = 0, COL2 = Cfg::N1, COL3 = 0;  // layer 3 reuses the columns of layers 1-2
-  const uint32_t aA = smem_u32(sA), aW1 = smem_u32(sW1), aW2 = smem_u32(sW2), aW3 = smem_u32(sW3);
-  uint32_t phase = 0;
+  const uint32_t aW1 = smem_u32(sW1), aW2 = smem_u32(sW2), aW3 = smem_u32(sW3);
+  uint32_t phase[2] = {0u, 0u};
+
+  // issue layer L (1..3) of buffer b; thread 0 only, after a __syncthreads
+  auto issue = [&](int L, int b) {
+    fence_after_sync();
+    const uint32_t aA = smem_u32(smem + b * Cfg::A_BYTES);
+    const uint32_t tb = tmem + b * Cfg::TMEM_COLS;
+    if (L == 1) {
+#pragma unroll
+      for (int ks = 0; ks < Cfg::K1P / 16; ++ks)
+        mma_bf16(tb, make_desc(aA + ks * 4096, 2048, 128), make_desc(aW1 + ks * 2 * (Cfg::N1 * 16), Cfg::N1 * 16, 128),
+                 IDESC1, ks > 0);
+    } else if (L == 2) {
+#pragma unroll
+      for (int ks = 0; ks < Cfg::N1 / 16; ++ks)
+        mma_bf16(tb + Cfg::N1, make_desc(aA + ks * 4096, 2048, 128),
+                 make_desc(aW2 + ks * 2 * (Cfg::N2 * 16), Cfg::N2 * 16, 128), IDESC2, ks > 0);
+    } else {
+#pragma unroll
+      for (int ks = 0; ks < Cfg::N2 / 16; ++ks)
+        mma_bf16(tb, make_desc(aA + ks * 4096, 2048, 128), make_desc(aW3 + ks * 2 * (Cfg::N3 * 16), Cfg::N3 * 16, 128),
+                 IDESC3, ks > 0);
+    }
+    mma_commit(mbar + b);
+  };
+  auto wait_mma = [&](int b) {
+    mbar_wait(mbar + b, phase[b]);
+    phase[b] ^= 1u;
+    fence_after_sync();
+  };
+  // all threads: make this thread's smem writes visible to the tensor core, then let thread 0 issue
+  auto publish_and_issue = [&](int L, int b) {
+    fence_proxy_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    if (tid == 0) issue(L, b);
+  };
 
   const int n_centres = a.B * Cfg::CPC;
   const int n_super = (n_centres + 127) / 128;
+  const int NS = a.NS;
   for (int st = blockIdx.x; st < n_super; st += gridDim.x) {
     const int cg = st * 128 + r;  // global centre index
     const bool live = cg < n_centres;
@@ -121,109 +166,138 @@ __global__ void __launch_bounds__(256, LEVEL == 1 ? 2 : 1) sa_mlp_kernel(const S
       const float *c = a.new_xyz + (size_t)cg * 3;
       cx = c[0]; cy = c[1]; cz = c[2];
     }
-    const int *my_idx = a.ball_idx + (size_t)cg * a.NS;
+    const int *my_idx = a.ball_idx + (size_t)cg * NS;
     float runmax[Cfg::N3 / 2];
 #pragma unroll
     for (int i = 0; i < Cfg::N3 / 2; ++i) runmax[i] = -INFINITY;
 
-    for (int s = 0; s < a.NS; ++s) {
-      // ---- gather row r = (centre cg, sample s) into the A tile -------------------------------------
+    // ---- gather of row r = (centre cg, sample s) into A buffer b, split in "load" (early) and "store" -----
+    struct Pre { int k; float v0, v1, v2, v3, v4, v5; };
+    auto preload = [&](int s) {
+      Pre p{0, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (live && s < NS) {
+        p.k = __ldg(my_idx + s);
+        if (LEVEL == 1) {
+          const float2 *q = reinterpret_cast<const float2 *>(a.pts + ((size_t)cloud * a.P + p.k) * 6);
+          const float2 p0 = __ldg(q), p1 = __ldg(q + 1), p2 = __ldg(q + 2);  // x y | z r | g b
+          p.v0 = p0.x; p.v1 = p0.y; p.v2 = p1.x; p.v3 = p1.y; p.v4 = p2.x; p.v5 = p2.y;
+        } else if (wg == 1) {
+          const float *q = a.pts + ((size_t)cloud * a.P + p.k) * 3;
+          p.v0 = __ldg(q); p.v1 = __ldg(q + 1); p.v2 = __ldg(q + 2);
+        }
+      }
+      return p;
+    };
+    auto gather_begin = [&](int b, const Pre &p) {
+      uint8_t *sA = smem + b * Cfg::A_BYTES;
       if (LEVEL == 1) {
         if (wg == 0) {
           uint4 row = make_uint4(0, 0, 0, 0);
           if (live) {
-            const int k = __ldg(my_idx + s);
-            const float2 *p = reinterpret_cast<const float2 *>(a.pts + ((size_t)cloud * a.P + k) * 6);
-            const float2 p0 = __ldg(p), p1 = __ldg(p + 1), p2 = __ldg(p + 2);  // x y | z r | g b
-            row.x = pack_bf16(p0.x - cx, p0.y - cy);
-            row.y = pack_bf16(p1.x - cz, p1.y);
-            row.z = pack_bf16(p2.x, p2.y);
+            row.x = pack_bf16(p.v0 - cx, p.v1 - cy);
+            row.y = pack_bf16(p.v2 - cz, p.v3);
+            row.z = pack_bf16(p.v4, p.v5);
           }
           *reinterpret_cast<uint4 *>(sA + tile_off(128, r, 0)) = row;
-          // columns 8..15 are K padding; the layer-1/2 epilogues reuse this space, so re-zero it every tile
+          // columns 8..15 are K padding that the layer-1/2 epilogues overwrite: re-zero every tile
           *reinterpret_cast<uint4 *>(sA + tile_off(128, r, 8)) = make_uint4(0, 0, 0, 0);
         }
       } else {
         // columns [0,KF) = features of the neighbour, [KF,KF+3) = xyz - centre (weights permuted to match)
-        int k = 0;
-        if (live) k = __ldg(my_idx + s);
         constexpr int CH = Cfg::KF / 8;  // 16-byte chunks of the feature row
-        const uint4 *f = reinterpret_cast<const uint4 *>(a.feat) + ((size_t)cloud * a.P + k) * CH;
+        const uint4 *f = reinterpret_cast<const uint4 *>(a.feat) + ((size_t)cloud * a.P + p.k) * CH;
 #pragma unroll
-        for (int q = wg * (CH / 2); q < (wg + 1) * (CH / 2); ++q) {
-          const uint4 v = live ? __ldg(f + q) : make_uint4(0, 0, 0, 0);
-          *reinterpret_cast<uint4 *>(sA + tile_off(128, r, q * 8)) = v;
+        for (int q = 0; q < CH / 2; ++q) {
+          const int qq = wg * (CH / 2) + q;
+          cp_async16(sA + tile_off(128, r, qq * 8), f + qq, live ? 16u : 0u);
         }
         if (wg == 1) {
           uint4 row = make_uint4(0, 0, 0, 0);
           if (live) {
-            const float *p = a.pts + ((size_t)cloud * a.P + k) * 3;
-            row.x = pack_bf16(__ldg(p) - cx, __ldg(p + 1) - cy);
-            row.y = pack_bf16(__ldg(p + 2) - cz, 0.f);
+            row.x = pack_bf16(p.v0 - cx, p.v1 - cy);
+            row.y = pack_bf16(p.v2 - cz, 0.f);
           }
           *reinterpret_cast<uint4 *>(sA + tile_off(128, r, Cfg::KF)) = row;
         }
       }
-      fence_proxy_async_smem();
-      fence_before_sync();
-      __syncthreads();
-      // ---- layer 1 ------------------------------------------------------------------------------------------
-      if (tid == 0) {
-        fence_after_sync();
+    };
+    auto gather_end = [&]() {
+      if (LEVEL != 1) cp_async_wait_all();
+    };
+    // relu(acc + shift) of layer L (1,2) of buffer b -> bf16 -> A buffer b (this thread: its row, half of the columns)
+    auto epi12 = [&](int L, int b) {
+      uint8_t *sA = smem + b * Cfg::A_BYTES;
+      const uint32_t tb = tmem + b * Cfg::TMEM_COLS + lane_off;
+      if (L == 1) {
 #pragma unroll
-        for (int ks = 0; ks < Cfg::K1P / 16; ++ks)
-          mma_bf16(tmem + COL1, make_desc(aA + ks * 2 * 2048, 2048, 128),
-                   make_desc(aW1 + ks * 2 * (Cfg::N1 * 16), Cfg::N1 * 16, 128), IDESC1, ks > 0);
-        mma_commit(mbar);
+        for (int c = 0; c < Cfg::N1 / 64; ++c) {
+          const int c0 = wg * (Cfg::N1 / 2) + c * 32;
+          epilogue_to_smem(tb + c0, sh1, sA, r, c0);
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < Cfg::N2 / 64; ++c) {
+          const int c0 = wg * (Cfg::N2 / 2) + c * 32;
+          epilogue_to_smem(tb + Cfg::N1 + c0, sh2, sA, r, c0);
+        }
       }
-      mbar_wait(mbar, phase);
-      phase ^= 1;
-      fence_after_sync();
-#pragma unroll
-      for (int c0 = wg * (Cfg::N1 / 2); c0 < (wg + 1) * (Cfg::N1 / 2); c0 += 32)
-        epilogue_to_smem(trow + COL1 + c0, sh1, sA, r, c0);
-      fence_proxy_async_smem();
-      fence_before_sync();
-      __syncthreads();
-      // ---- layer 2 ------------------------------------------------------------------------------------------
-      if (tid == 0) {
-        fence_after_sync();
-#pragma unroll
-        for (int ks = 0; ks < Cfg::N1 / 16; ++ks)
-          mma_bf16(tmem + COL2, make_desc(aA + ks * 2 * 2048, 2048, 128),
-                   make_desc(aW2 + ks * 2 * (Cfg::N2 * 16), Cfg::N2 * 16, 128), IDESC2, ks > 0);
-        mma_commit(mbar);
-      }
-      mbar_wait(mbar, phase);
-      phase ^= 1;
-      fence_after_sync();
-#pragma unroll
-      for (int c0 = wg * (Cfg::N2 / 2); c0 < (wg + 1) * (Cfg::N2 / 2); c0 += 32)
-        epilogue_to_smem(trow + COL2 + c0, sh2, sA, r, c0);
-      fence_proxy_async_smem();
-      fence_before_sync();
-      __syncthreads();
-      // ---- layer 3 + running max over the neighbourhood -----------------------------------------------------
-      if (tid == 0) {
-        fence_after_sync();
-#pragma unroll
-        for (int ks = 0; ks < Cfg::N2 / 16; ++ks)
-          mma_bf16(tmem + COL3, make_desc(aA + ks * 2 * 2048, 2048, 128),
-                   make_desc(aW3 + ks * 2 * (Cfg::N3 * 16), Cfg::N3 * 16, 128), IDESC3, ks > 0);
-        mma_commit(mbar);
-      }
-      mbar_wait(mbar, phase);
-      phase ^= 1;
-      fence_after_sync();
+    };
+    auto epi3 = [&](int b) {
+      const uint32_t tb = tmem + b * Cfg::TMEM_COLS + lane_off + wg * (Cfg::N3 / 2);
 #pragma unroll
       for (int cc = 0; cc < Cfg::N3 / 64; ++cc) {
         float v[32];
-        tmem_ld32(trow + COL3 + wg * (Cfg::N3 / 2) + cc * 32, v);
+        tmem_ld32(tb + cc * 32, v);
 #pragma unroll
         for (int i = 0; i < 32; ++i) runmax[cc * 32 + i] = fmaxf(runmax[cc * 32 + i], v[i]);
       }
-      // (the next gather overwrites sA / the next MMA overwrites TMEM only after the __syncthreads that follows it)
+    };
+
+    // ---- prologue: tiles s = 0 and s = 1 -------------------------------------------------------------------
+    {
+      const Pre p0 = preload(0), p1 = preload(1);
+      gather_begin(0, p0);
+      if (1 < NS) gather_begin(1, p1);
+      gather_end();
+      fence_proxy_async_smem();
       fence_before_sync();
+      __syncthreads();
+      if (tid == 0) {
+        issue(1, 0);
+        if (1 < NS) issue(1, 1);
+      }
+    }
+    for (int s = 0; s < NS; s += 2) {
+      const bool has1 = s + 1 < NS;
+      const Pre n0 = preload(s + 2), n1 = preload(s + 3);  // raw data of the next pair, consumed at the end of this one
+#pragma unroll
+      for (int L = 1; L <= 2; ++L) {
+        wait_mma(0);
+        epi12(L, 0);
+        publish_and_issue(L + 1, 0);
+        if (has1) {
+          wait_mma(1);
+          epi12(L, 1);
+          publish_and_issue(L + 1, 1);
+        }
+      }
+      // layer 3 done: A buffer free -> start the next gather, take the running max, hand the next tile to the tensor pipe
+      wait_mma(0);
+      if (s + 2 < NS) gather_begin(0, n0);
+      epi3(0);
+      if (s + 2 < NS) {
+        gather_end();
+        publish_and_issue(1, 0);
+      }
+      if (has1) {
+        wait_mma(1);
+        if (s + 3 < NS) gather_begin(1, n1);
+        epi3(1);
+        if (s + 3 < NS) {
+          gather_end();
+          publish_and_issue(1, 1);
+        }
+      }
     }
     // ---- finalize: relu(max + shift3) -> bf16 row of this centre -------------------------------------------
     if (live) {
@@ -241,10 +315,13 @@ __global__ void __launch_bounds__(256, LEVEL == 1 ? 2 : 1) sa_mlp_kernel(const S
         o[q] = make_uint4(w[0], w[1], w[2], w[3]);
       }
     }
+    // the next super-tile's first MMA overwrites TMEM that this one's last epilogue read
+    fence_before_sync();
+    __syncthreads();
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<Cfg::TMEM_COLS>(tmem);
+  if (warp == 1) tmem_dealloc<2 * Cfg::TMEM_COLS>(tmem);
 }
 
 using Sa1 = SaCfg<3, 16, 64, 64, 128, 32>;
@@ -261,7 +338,7 @@ int launch_sa(const SaMlpArgs &a, cudaStream_t st) {
   rc = sv::cuda_status(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, Cfg::SMEM_BYTES));
   if (rc) return rc;
   if (per_sm < 1) per_sm = 1;
-  if (per_sm * Cfg::TMEM_COLS > 512) per_sm = 512 / Cfg::TMEM_COLS;  // TMEM columns are not part of the occupancy query
+  if (per_sm * 2 * Cfg::TMEM_COLS > 512) per_sm = 512 / (2 * Cfg::TMEM_COLS);  // TMEM columns are not part of the occupancy query
   const int n_super = (a.B * Cfg::CPC + 127) / 128;
   int grid = sms * per_sm;
   if (grid > n_super) grid = n_super;

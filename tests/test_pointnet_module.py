@@ -1,0 +1,109 @@
+"""PointNetPP module: state_dict contract (CPU) and parity of the fused tcgen05 path (GPU) against
+(a) the reference's own modules run on CPU in fp32 (tests/golden/model_pointnetpp.npz, made by
+oracle/make_golden_model.py) and (b) the generic path (reference operator sequence on the native
+point ops + cuDNN fp32) on the same GPU."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from sceneverse_b200 import synthetic, weights
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def make_net():
+    from sceneverse_b200.modules.pointnet import GPS_SPEC, PointNetPP
+    net = PointNetPP(**GPS_SPEC).eval()
+    net.load_state_dict(weights.synthetic_state_dict(net, seed=0))
+    return net
+
+
+def test_state_dict_matches_reference_contract():
+    want = json.load(open(os.path.join(GOLDEN, "state_dict_shapes.json")))["PointNetPP"]
+    got = {k: list(v.shape) for k, v in make_net().state_dict().items()}
+    assert got == want
+
+
+def rel_err(got, want):
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    return float(np.abs(got - want).max() / (np.abs(want).max() + 1e-12)), \
+        float(np.abs(got - want).mean() / (np.abs(want).mean() + 1e-12))
+
+
+@pytest.mark.gpu
+def test_generic_path_matches_reference_fp32():
+    """Reference operator sequence on the native kernels, fp32 (TF32 off): 1e-5-level parity with the reference on CPU."""
+    z = np.load(os.path.join(GOLDEN, "model_pointnetpp.npz"))
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    net = make_net().cuda()
+    x = torch.from_numpy(synthetic.object_batch(int(z["input_seed"]), int(z["n_clouds"]), 1024,
+                                                float(z["pad_fraction"]))).cuda()
+    with torch.no_grad():
+        y = net.forward_generic(x)
+    mx, mean = rel_err(y.cpu().numpy(), z["out"])
+    assert mx < 1e-4 and mean < 1e-5, (mx, mean)  # fp32, different summation order only
+
+
+@pytest.mark.gpu
+def test_fused_path_indices_and_features():
+    z = np.load(os.path.join(GOLDEN, "model_pointnetpp.npz"))
+    net = make_net().cuda()
+    x = torch.from_numpy(synthetic.object_batch(int(z["input_seed"]), int(z["n_clouds"]), 1024,
+                                                float(z["pad_fraction"]))).cuda()
+    with torch.no_grad():
+        assert net.fused_available(x)
+    for p in net.parameters():  # the frozen-backbone configuration of all_pretrain.yaml
+        p.requires_grad = False
+    assert net.fused_available(x)
+    y, inter = net.forward_fused(x, return_intermediates=True)
+    # sampling is index work: the sampled centres must be bit-identical to the reference's
+    np.testing.assert_array_equal(inter["new_xyz"].cpu().numpy(), z["new_xyz1"])
+    np.testing.assert_array_equal(inter["new_xyz2"].cpu().numpy(), z["new_xyz2"])
+    # features: bf16 tensor-core math vs the fp32 reference (tolerances: bf16 operand rounding through 3/6/9 layers)
+    f1 = inter["feat1"].float().transpose(1, 2).cpu().numpy()  # (B,128,32) like the reference
+    f2 = inter["feat2"].float().transpose(1, 2).cpu().numpy()
+    e1, e2, e3 = rel_err(f1, z["feat1"]), rel_err(f2, z["feat2"]), rel_err(y.cpu().numpy(), z["out"])
+    print("rel err (max/max, mean/mean): SA1", e1, "SA2", e2, "out", e3)
+    assert e1[0] < 2e-2 and e1[1] < 5e-3, e1
+    assert e2[0] < 3e-2 and e2[1] < 8e-3, e2
+    assert e3[0] < 4e-2 and e3[1] < 1e-2, e3
+
+
+@pytest.mark.gpu
+def test_sa_kernels_against_bf16_emulation():
+    """Tight check of the two tcgen05 kernels: same bf16-rounded operands, fp32 accumulation in torch."""
+    import torch.nn.functional as F
+    from sceneverse_b200.modules.pointnet import fold_bn
+    net = make_net().cuda()
+    x = torch.from_numpy(synthetic.object_batch(11, 37, 1024, 0.2)).cuda()  # 37 clouds: partial last super-tile
+    y, it = net.forward_fused(x, return_intermediates=True)
+    bf = lambda t: t.to(torch.bfloat16).float()
+
+    def emulate(rows, mlp):  # rows (..., K) f32 already bf16-rounded
+        h = rows
+        for j in range(3):
+            layer = getattr(mlp, f"layer{j}")
+            w, s = fold_bn(layer.conv.weight, layer.bn.bn)
+            h = torch.relu(h @ bf(w).t() + s)
+            if j < 2:
+                h = bf(h)
+        return bf(h.max(dim=-2).values)
+
+    B = x.shape[0]
+    idx = it["ball_idx"].long()                                               # (B,32,32)
+    g = torch.gather(x[:, None].expand(B, 32, 1024, 6), 2, idx[..., None].expand(B, 32, 32, 6))
+    g = torch.cat([g[..., :3] - it["new_xyz"][:, :, None], g[..., 3:]], -1)
+    want1 = emulate(bf(g), net.encoder[0].mlps[0])                            # (B,32,128)
+    got1 = it["feat1"].float()
+    assert (got1 - want1).abs().max().item() <= 2e-2 * want1.abs().max().item()
+    idx2 = it["ball_idx2"].long()                                             # (B,16,32) into the 32 level-1 points
+    gx = torch.gather(it["new_xyz"][:, None].expand(B, 16, 32, 3), 2, idx2[..., None].expand(B, 16, 32, 3))
+    gf = torch.gather(got1[:, None].expand(B, 16, 32, 128), 2, idx2[..., None].expand(B, 16, 32, 128))
+    rows2 = torch.cat([bf(gx - it["new_xyz2"][:, :, None]), gf], -1)          # reference order [xyz | feat]
+    want2 = emulate(rows2, net.encoder[1].mlps[0])
+    got2 = it["feat2"].float()
+    assert (got2 - want2).abs().max().item() <= 2e-2 * want2.abs().max().item()
