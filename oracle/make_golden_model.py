@@ -41,9 +41,66 @@ def golden_pointnetpp():
     return {k: list(v.shape) for k, v in net.state_dict().items()}
 
 
+def _load(m, seed=0):
+    m.load_state_dict(weights.synthetic_state_dict(m, seed=seed))
+    return m.eval()
+
+
+def golden_gps_stack():
+    """Config-1-like parity gate (BASELINE.json configs[0]): B=2 scenes x 32 object slots (second scene padded),
+    P=1024, L=50; language features are seeded random (BERT is upstream of the path)."""
+    import tempfile
+    from modules.build import GROUNDING_REGISTRY, HEADS_REGISTRY, VISION_REGISTRY
+    import importlib
+    import types
+    CL = importlib.import_module("optim.loss.contra_loss")
+    LL = importlib.import_module("optim.loss.loss")
+    og3d_loss, lm_cls_loss = LL.og3d_loss, LL.lm_cls_loss
+    d = synthetic.scene_batch(21, B=2, O=32, P=1024, L=50, Ls=300, min_obj=12)
+    t = {k: torch.from_numpy(v) for k, v in d.items()}
+    g = torch.Generator().manual_seed(5)
+    txt = torch.randn(2, 50, 768, generator=g) * 0.5
+    scene_txt = torch.randn(2, 768, generator=g) * 0.5
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp, torch.no_grad(), ref_shims.cpu_cuda_identity():
+        ref_shims.write_text_features(tmp, weights.synthetic_tensor("text_features", (607, 768)))
+        enc = _load(VISION_REGISTRY.get("PointOpenVocabEncoder")(None, lang_path=tmp, freeze=True))
+        obj, obj_pre, sem = enc(t["obj_fts"], t["obj_locs"], t["obj_masks"], t["obj_sem_masks"], t["obj_labels"], 1, 1)
+        out.update(vis_obj=obj.numpy(), vis_obj_pre=obj_pre.numpy(), vis_sem_cls=sem.numpy()[:, :, :64],
+                   vis_sem_cls_argmax=sem.argmax(-1).numpy())
+        v2 = _load(GROUNDING_REGISTRY.get("UnifiedSpatialCrossEncoderV2")(None), 1)
+        t2, o2 = v2(txt, t["txt_masks"], obj, t["obj_locs"], t["obj_masks"])
+        out.update(v2_txt=t2.numpy(), v2_obj=o2.numpy())
+        v1 = _load(GROUNDING_REGISTRY.get("UnifiedSpatialCrossEncoderV1")(None), 2)
+        t1, o1 = v1(txt, t["txt_masks"], obj, t["obj_locs"], t["obj_masks"])
+        out.update(v1_txt=t1.numpy(), v1_obj=o1.numpy())
+        en = _load(GROUNDING_REGISTRY.get("EntitySpatialCrossEncoder")(None), 3)
+        _, oe = en(txt, t["txt_masks"], obj, t["obj_locs"], t["obj_masks"])
+        out.update(entity_obj=oe.numpy())
+        gh = _load(HEADS_REGISTRY.get("GroundHeadV1")(None, input_size=768, hidden_size=384, sem_cls_size=607), 4)
+        a, b, c, dd = gh(t2, o2, obj_pre, t["obj_masks"])
+        out.update(gh_txt_cls=a.numpy(), gh_obj_cls=b.numpy()[:, :, :64], gh_obj_cls_pre=c.numpy()[:, :, :64], gh_og3d=dd.numpy())
+        ph = _load(HEADS_REGISTRY.get("OVPretrainHead")(None), 5)
+        lm, ol = ph(t2, o2)
+        out.update(ph_txt_lm_slice=lm.numpy()[:, :, :128], ph_txt_lm_rowsum=lm.sum(-1).numpy(), ph_obj_lm=ol.numpy()[:, :, :64])
+        # losses (num_gpu = 1 -> no gather), data_dict keys as OpenVocab.forward fills them (openvocab.py:52-74)
+        dd_ = dict(t)
+        dd_.update(intra_obj_embeds=o2, intra_text_embed=t2[:, 0], inter_obj_embeds=obj, inter_text_embed=txt[:, 0],
+                   scene_embed=obj.mean(dim=1), scene_text_embed=scene_txt, og3d_logits=dd.clone(),
+                   txt_lm_cls_logits=lm)
+        cfg = types.SimpleNamespace(num_gpu=1, task="Pretrain")
+        out.update(loss_within=CL.TextObjWithinBatch(cfg)(dict(dd_, intra_obj_embeds=o2.clone())).numpy(),
+                   loss_obj_between=CL.TextObjBetweenBatch(cfg)(dd_).numpy(),
+                   loss_scene_between=CL.TextSceneBetweenBatch(cfg)(dd_).numpy(),
+                   loss_og3d=og3d_loss(dd_).numpy(), loss_lm=lm_cls_loss(dd_).numpy())
+    np.savez_compressed(os.path.join(OUT, "model_gps_stack.npz"), data_seed=21, txt_seed=5, **out)
+    print({k: (v.shape if hasattr(v, "shape") else v) for k, v in out.items()})
+
+
 def main():
     ref_shims.install()
     torch.manual_seed(0)
+    golden_gps_stack()
     shapes = {"PointNetPP": golden_pointnetpp()}
     # state_dict contracts of the registry classes (SURVEY.md §8b): key -> shape
     from modules.build import GROUNDING_REGISTRY, HEADS_REGISTRY, VISION_REGISTRY

@@ -79,3 +79,49 @@ def adversarial_clouds(seed, N):
         rng.uniform(0.9999, 1.0001, size=(N // 2, 1)).astype(np.float32)
     out["skip_boundary"] = boundary.astype(np.float32)
     return out
+
+
+def scene_batch(seed, B=64, O=80, P=1024, L=50, Ls=300, min_obj=8, all_valid=False):
+    """Synthetic `data_dict` with the key set / dtypes of the reference's dataset wrappers
+    (data/datasets/dataset_wrapper.py:38-111,147-195), as numpy arrays:
+    txt_ids/txt_masks (B,L) int64, obj_fts (B,O,P,6) f32 (padded objects all 1.0), obj_locs (B,O,6) f32 (pad 0),
+    obj_masks/obj_sem_masks (B,O) bool, obj_labels (B,O) int64 (pad -100), tgt_object_id (B,1) int64,
+    masked_lm_labels (B,L) int64 (-1 = ignore), scene_txt_ids/scene_txt_masks (B,Ls) int64."""
+    rng = np.random.default_rng(seed)
+    d = {}
+    n_obj = np.full(B, O) if all_valid else rng.integers(min(min_obj, O), O + 1, size=B)
+    obj_fts = np.ones((B, O, P, 6), np.float32)
+    obj_locs = np.zeros((B, O, 6), np.float32)
+    obj_masks = np.zeros((B, O), bool)
+    obj_labels = np.full((B, O), -100, np.int64)
+    for b in range(B):
+        n = int(n_obj[b])
+        for o in range(n):
+            obj_fts[b, o] = object_cloud(rng, P)
+        obj_locs[b, :n, 0:2] = rng.uniform(-4, 4, size=(n, 2))
+        obj_locs[b, :n, 2] = rng.uniform(0, 2.5, size=n)
+        obj_locs[b, :n, 3:] = rng.uniform(0.1, 2.0, size=(n, 3))
+        obj_masks[b, :n] = True
+        obj_labels[b, :n] = rng.integers(0, 607, size=n)
+    d["obj_fts"], d["obj_locs"], d["obj_masks"], d["obj_labels"] = obj_fts, obj_locs, obj_masks, obj_labels
+    d["obj_sem_masks"] = obj_masks & (rng.random((B, O)) > 0.25)
+    d["tgt_object_id"] = np.array([[rng.integers(0, n)] for n in n_obj], np.int64)
+
+    def text(length):
+        ids = np.zeros((B, length), np.int64)
+        masks = np.zeros((B, length), np.int64)
+        for b in range(B):
+            ell = int(rng.integers(min(8, length), length + 1))
+            ids[b, :ell] = rng.integers(1000, 30000, size=ell)
+            ids[b, 0], ids[b, ell - 1] = 101, 102
+            masks[b, :ell] = 1
+        return ids, masks
+
+    d["txt_ids"], d["txt_masks"] = text(L)
+    lm = np.full((B, L), -1, np.int64)
+    pick = (rng.random((B, L)) < 0.15) & (d["txt_masks"] == 1)
+    pick[:, 1] = True  # at least one supervised position per sample
+    lm[pick] = d["txt_ids"][pick]
+    d["masked_lm_labels"] = lm
+    d["scene_txt_ids"], d["scene_txt_masks"] = text(Ls)
+    return d

@@ -1,0 +1,147 @@
+"""Parity of the B200 GPS modules with the reference's own modules (goldens: tests/golden/model_gps_stack.npz,
+produced by running the UNMODIFIED reference classes on CPU in fp32, oracle/make_golden_model.py).
+CPU tests cover the host logic of the attention stack / heads / losses at fp32 (1e-5); the GPU tests run the whole
+chain including the native PointNet++ path."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from sceneverse_b200 import synthetic, weights
+from sceneverse_b200.modules import grounding, heads, losses, registry, vision
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+Z = np.load(os.path.join(GOLDEN, "model_gps_stack.npz"))
+
+
+def load(m, seed):
+    m.load_state_dict(weights.synthetic_state_dict(m, seed=seed))
+    return m.eval()
+
+
+def inputs(device="cpu"):
+    d = synthetic.scene_batch(int(Z["data_seed"]), B=2, O=32, P=1024, L=50, Ls=300, min_obj=12)
+    t = {k: torch.from_numpy(v).to(device) for k, v in d.items()}
+    g = torch.Generator().manual_seed(int(Z["txt_seed"]))
+    txt = (torch.randn(2, 50, 768, generator=g) * 0.5).to(device)
+    scene_txt = (torch.randn(2, 768, generator=g) * 0.5).to(device)
+    return t, txt, scene_txt
+
+
+def close(got, want, tol, what):
+    got = got.detach().float().cpu().numpy()
+    scale = np.abs(want[np.isfinite(want)]).max() + 1e-12
+    fin = np.isfinite(want)
+    assert (np.isfinite(got) == fin).all(), what
+    err = np.abs(got[fin] - want[fin]).max() / scale
+    assert err < tol, f"{what}: max err / max|ref| = {err:.3e} (tol {tol})"
+    return err
+
+
+@pytest.mark.parametrize("name", ["PointOpenVocabEncoder", "UnifiedSpatialCrossEncoderV2", "UnifiedSpatialCrossEncoderV1",
+                                  "EntitySpatialCrossEncoder", "GroundHeadV1", "GroundHead", "PretrainHeadV1",
+                                  "OVPretrainHead"])
+def test_state_dict_contracts(name):
+    want = json.load(open(os.path.join(GOLDEN, "state_dict_shapes.json")))[name]
+    tf = weights.synthetic_tensor("text_features", (607, 768))
+    kw = {"PointOpenVocabEncoder": dict(freeze=True, text_features=tf),
+          "GroundHeadV1": dict(input_size=768, hidden_size=384, sem_cls_size=607)}.get(name, {})
+    reg = registry.VISION_REGISTRY if name in registry.VISION_REGISTRY else \
+        registry.GROUNDING_REGISTRY if name in registry.GROUNDING_REGISTRY else registry.HEADS_REGISTRY
+    m = reg.get(name)(None, **kw)
+    assert {k: list(v.shape) for k, v in m.state_dict().items()} == want
+
+
+def run_stack(device, obj, obj_pre, tol):
+    t, txt, scene_txt = inputs(device)
+    errs = {}
+    with torch.no_grad():
+        v2 = load(grounding.UnifiedSpatialCrossEncoderV2(None), 1).to(device)
+        t2, o2 = v2(txt, t["txt_masks"], obj, t["obj_locs"], t["obj_masks"])
+        errs["v2_txt"] = close(t2, Z["v2_txt"], tol, "V2 txt")
+        errs["v2_obj"] = close(o2, Z["v2_obj"], tol, "V2 obj")
+        v1 = load(grounding.UnifiedSpatialCrossEncoderV1(None), 2).to(device)
+        t1, o1 = v1(txt, t["txt_masks"], obj, t["obj_locs"], t["obj_masks"])
+        errs["v1_txt"] = close(t1, Z["v1_txt"], tol, "V1 txt")
+        errs["v1_obj"] = close(o1, Z["v1_obj"], tol, "V1 obj")
+        en = load(grounding.EntitySpatialCrossEncoder(None), 3).to(device)
+        _, oe = en(txt, t["txt_masks"], obj, t["obj_locs"], t["obj_masks"])
+        errs["entity"] = close(oe, Z["entity_obj"], tol, "Entity obj")
+        gh = load(heads.GroundHeadV1(None, input_size=768, hidden_size=384, sem_cls_size=607), 4).to(device)
+        a, b, c, og = gh(t2, o2, obj_pre, t["obj_masks"])
+        errs["gh_txt"] = close(a, Z["gh_txt_cls"], tol, "GroundHeadV1 txt_cls")
+        close(b[:, :, :64], Z["gh_obj_cls"], tol, "GroundHeadV1 obj_cls")
+        close(c[:, :, :64], Z["gh_obj_cls_pre"], tol, "GroundHeadV1 obj_cls_pre")
+        errs["og3d"] = close(og, Z["gh_og3d"], tol, "og3d logits")  # north_star: grounding logits within 1e-3
+        ph = load(heads.OVPretrainHead(None), 5).to(device)
+        lm, ol = ph(t2, o2)
+        errs["lm"] = close(lm[:, :, :128], Z["ph_txt_lm_slice"], tol, "LM logits")
+        close(lm.sum(-1), Z["ph_txt_lm_rowsum"], tol * 30, "LM logits row sums")
+        close(ol[:, :, :64], Z["ph_obj_lm"], tol, "obj LM logits")
+        dd = dict(t)
+        dd.update(intra_obj_embeds=o2, intra_text_embed=t2[:, 0], inter_obj_embeds=obj, inter_text_embed=txt[:, 0],
+                  scene_embed=obj.mean(dim=1), scene_text_embed=scene_txt, og3d_logits=og, txt_lm_cls_logits=lm)
+        cfg = {"num_gpu": 1}
+        for key, fn in [("loss_within", losses.TextObjWithinBatch(cfg)), ("loss_obj_between", losses.TextObjBetweenBatch(cfg)),
+                        ("loss_scene_between", losses.TextSceneBetweenBatch(cfg)), ("loss_og3d", losses.og3d_loss),
+                        ("loss_lm", losses.lm_cls_loss)]:
+            if isinstance(fn, torch.nn.Module):
+                fn = fn.to(device)
+            got = float(fn(dd))
+            want = float(Z[key])
+            assert abs(got - want) <= tol * 10 * max(1.0, abs(want)), (key, got, want)
+    return errs
+
+
+def test_attention_stack_heads_losses_cpu_fp32():
+    """Host logic on CPU, fed with the reference's own object embeddings: fp32 tolerance 1e-5 (north_star)."""
+    obj = torch.from_numpy(Z["vis_obj"])
+    obj_pre = torch.from_numpy(Z["vis_obj_pre"])
+    errs = run_stack("cpu", obj, obj_pre, 1e-5)
+    print(errs)
+
+
+def test_calc_pairwise_locs_properties():
+    from sceneverse_b200 import ops
+    t, _, _ = inputs()
+    locs = ops.calc_pairwise_locs(t["obj_locs"][:, :, :3], t["obj_locs"][:, :, 3:])
+    assert locs.shape == (2, 32, 32, 5)
+    assert torch.allclose(locs[..., 0].amax(dim=(1, 2)), torch.ones(2))          # normalised by the max distance
+    assert torch.allclose(locs[..., 1] ** 2 + locs[..., 2] ** 2, torch.ones(2, 32, 32), atol=1e-3)  # sin^2+cos^2 (eps inside sqrt)
+    assert torch.allclose(locs[..., 0], locs[..., 0].transpose(1, 2))
+
+
+@pytest.mark.gpu
+def test_full_chain_gpu_generic_fp32():
+    """Vision encoder through the reference operator sequence on the native point ops (fp32, TF32 off) + stack: 1e-5 class."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    t, txt, _ = inputs("cuda")
+    tf = weights.synthetic_tensor("text_features", (607, 768))
+    enc = load(vision.PointOpenVocabEncoder(None, freeze=True, text_features=tf), 0).cuda()
+    enc.point_feature_extractor.fused_available = lambda x: False  # force the generic path
+    with torch.no_grad():
+        obj, obj_pre, sem = enc(t["obj_fts"], t["obj_locs"], t["obj_masks"], t["obj_sem_masks"], t["obj_labels"], 1, 1)
+    close(obj_pre, Z["vis_obj_pre"], 2e-5, "PointNet++ embeddings (generic path)")
+    close(obj, Z["vis_obj"], 5e-5, "spatial encoder output")
+    assert (sem.argmax(-1).cpu().numpy() == Z["vis_sem_cls_argmax"]).mean() > 0.98
+    errs = run_stack("cuda", obj, obj_pre, 1e-4)
+    print(errs)
+
+
+@pytest.mark.gpu
+def test_full_chain_gpu_fused_bf16():
+    """Same chain with the fused tcgen05 PointNet++ path (bf16 operands): bf16-level tolerance vs the fp32 reference."""
+    t, txt, _ = inputs("cuda")
+    tf = weights.synthetic_tensor("text_features", (607, 768))
+    enc = load(vision.PointOpenVocabEncoder(None, freeze=True, text_features=tf), 0).cuda()
+    with torch.no_grad():
+        assert enc.point_feature_extractor.fused_available(t["obj_fts"].view(-1, 1024, 6))
+        obj, obj_pre, sem = enc(t["obj_fts"], t["obj_locs"], t["obj_masks"], t["obj_sem_masks"], t["obj_labels"], 1, 1)
+    e1 = close(obj_pre, Z["vis_obj_pre"], 2e-2, "PointNet++ embeddings (fused bf16)")
+    e2 = close(obj, Z["vis_obj"], 2e-2, "spatial encoder output (fused bf16 backbone)")
+    print("fused bf16 backbone: obj_pre err", e1, "obj err", e2)
+    errs = run_stack("cuda", obj, obj_pre, 2e-2)
+    print(errs)
