@@ -1,18 +1,21 @@
 #!/usr/bin/env python
-"""bench.py — contract in the task statement (one JSON line on rank 0).
+"""bench.py — one JSON line on rank 0 (contract in the task statement).
 
-Workloads (config.workload):
-  pointops_sa1   the set-abstraction sampling/grouping front of the GPS object encoder at the
-                 model shape of configs/final/all_pretrain.yaml: B*O = 64 scenes x 80 objects =
-                 5120 clouds x 1024 points per GPU step; one step = fused FPS(32) + ball_query
-                 (r=0.2, nsample=32) over the batch (SURVEY.md §8d "model shape", the gated
-                 FPS+ball_query figure).  Metric: Mpts/s (= B*N / t), also given as scenes/s.
+Workload (config.workload):
+  gps_pretrain  (default)  BASELINE.json configs[3] on one node: the full GPS pre-training step of
+      configs/final/all_pretrain.yaml (+TextObjBetweenBatch): B = 64 scenes/GPU x 80 object slots x 1024 points,
+      50-token captions + 300-token scene captions; BERT-4L -> PointNet++ (frozen, native fused path) -> 4 spatial
+      layers -> 4 joint layers -> OVPretrainHead -> lm_cls + 3 contrastive losses -> backward -> clip -> AdamW,
+      bf16 autocast, data-parallel over scenes (NCCL gradient all-reduce + embedding all-gather).
+      Metric: scenes/s (whole job).  `e2e` = the same step fed from pinned HOST buffers (H2D of the whole data_dict
+      inside the timed region) with the loss read back.
+  pointops_sa1  (--workload pointops_sa1)  the FPS+ball_query front alone at the model shape (5120 x 1024), Mpts/s.
 
-A "step" processes one batch already resident in HBM (`value`) or, for `e2e`, starting from
-pinned HOST buffers through the public `_ext` API with the result copied back to the host.
-Inputs are rotated over enough distinct device buffers to exceed the 126 MB L2.
-`--impl reference` times the CPU oracle (the reference has no CPU path for these ops,
-sampling.cpp:34) on a bounded sample with all host threads.
+Every default run also measures the two gated kernels in isolation (CUDA events) and reports their rooflines:
+  roofline           sa2_mlp tcgen05 kernel, tensor bound, vs measured bf16 TFLOP/s
+  roofline_pointops  sa_sample kernel (FPS + ball query), HBM bound, vs measured copy GB/s
+`--impl reference` times the CPU path (host cores) on a bounded sample: the same modules on CPU with the CPU oracle
+standing in for the CUDA-only point ops (the reference has no CPU implementation of them, sampling.cpp:34).
 """
 import argparse
 import json
@@ -27,26 +30,26 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-SCENES, OBJS, PTS = 64, 80, 1024
+SCENES, OBJS, PTS, TXT, SCENE_TXT = 64, 80, 1024, 50, 300
 NPOINT, RADIUS, NSAMPLE = 32, 0.2, 32
-# unfused accounting, fixed definition: FPS (12N+4m) + ball query (12N+12M+4*M*ns)
-ALG_BYTES_PER_CLOUD = (12 * PTS + 4 * NPOINT) + (12 * PTS + 12 * NPOINT + 4 * NPOINT * NSAMPLE)  # 29,184
+# unfused accounting, fixed definition: FPS (12N+4m) + ball query (12N+12M+4*M*ns) = 29,184 B / cloud
+ALG_BYTES_PER_CLOUD = (12 * PTS + 4 * NPOINT) + (12 * PTS + 12 * NPOINT + 4 * NPOINT * NSAMPLE)
+SA2_FLOPS_PER_CLOUD = 2 * 512 * (131 * 128 + 128 * 128 + 128 * 256)  # algorithmic (unpadded K) flops of the SA2 MLP
+METRIC = "GPS pre-train scenes/sec"
 
 
-def measured_peaks():
+def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
-    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+        return float(d["hbm_gbs"]), float(d["bf16_tflops"]), "measured (MEASURED_PEAKS.json: copy GB/s, cuBLAS bf16 burst)"
+    return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index, self.rows, self.stop = index, [], threading.Event()
@@ -78,161 +81,243 @@ class ClockSampler:
         sm = sorted(float(r[0]) for r in self.rows)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
+        pw = [float(r[2]) for r in self.rows if r[2].replace(".", "", 1).isdigit()]
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "samples": len(self.rows)}
+                "samples": len(self.rows), "power_w_max": max(pw) if pw else None}
 
 
-def make_clouds(seed, n_clouds):
+def make_scene_batches(n_batches, scenes, seed0):
+    """Distinct synthetic batches; object clouds are drawn from a pool of 512 synthetic objects (generation cost)."""
     from sceneverse_b200 import synthetic
-    # one third of the object slots are padding (all-ones), as in a real batch (n_obj ~ U{8..80})
-    return np.ascontiguousarray(synthetic.object_batch(seed, n_clouds, PTS, pad_fraction=0.3)[:, :, :3])
+    out = []
+    for i in range(n_batches):
+        d = synthetic.scene_batch(seed0 + 1000 * i, B=scenes, O=OBJS, P=8, L=TXT, Ls=SCENE_TXT)  # layout only (P=8 is a stub)
+        pool = synthetic.object_batch(seed0 + 1000 * i + 7, 512, PTS)
+        rng = np.random.default_rng(seed0 + i)
+        fts = np.ones((scenes, OBJS, PTS, 6), np.float32)
+        pick = rng.integers(0, 512, size=(scenes, OBJS))
+        m = d["obj_masks"]
+        fts[m] = pool[pick[m]]
+        d["obj_fts"] = fts
+        out.append(d)
+    return out
 
 
-def cpu_reference_arm(steps, warmup, sample_clouds=SCENES * OBJS):
-    """Times the CPU oracle (all host threads, OpenMP over clouds) on a bounded sample."""
-    from oracle import pointops_ref as R
-    R.build()
-    xyz = make_clouds(42, sample_clouds)
-    cores = os.cpu_count()
+def cpu_reference_step_fn(scenes):
+    """The GPS step on CPU: same host modules, CPU oracle as `_ext` (bench-only use of oracle/)."""
+    import torch
+    from oracle import pointops_ref
+    from sceneverse_b200 import model as M, pointnet2_utils, train, weights
+    pointops_ref.build()
+    pointnet2_utils._ext = pointops_ref.RefExt()  # CPU stand-in for the CUDA-only operators, this process only
+    torch.set_num_threads(os.cpu_count())
+    tf = weights.synthetic_tensor("text_features", (607, 768))
+    ps = train.PretrainStep(M.pretrain_config(1, text_features=tf), "cpu", dtype=torch.float32)
+    batch = {k: torch.from_numpy(v) for k, v in make_scene_batches(1, scenes, 42)[0].items()}
+    return lambda: float(ps.step(dict(batch)))
 
-    def step():
-        idx = R.furthest_point_sampling(xyz, NPOINT)
-        new_xyz = np.take_along_axis(xyz, idx[:, :, None].astype(np.int64).repeat(3, 2), 1)
-        R.ball_query(new_xyz, xyz, RADIUS, NSAMPLE)
 
-    for _ in range(max(1, min(warmup, 1))):
-        step()
+def run_reference(args, config):
+    scenes = 2
+    step = cpu_reference_step_fn(scenes)
+    steps = max(1, min(args.steps, 3))
+    step()
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
     dt = (time.perf_counter() - t0) / steps
-    mpts = sample_clouds * PTS / dt / 1e6
-    return mpts, dt, {"value": mpts, "unit": "Mpts/s", "cores": cores, "kind": "port",
-                      "sample": f"{sample_clouds} clouds x {PTS} pts per step (of {SCENES * OBJS}), FPS m={NPOINT} + "
-                                f"ball_query r={RADIUS} ns={NSAMPLE}, oracle/pointops_ref.c with OpenMP over clouds"}
+    val = scenes / dt
+    cb = {"value": val, "unit": "scenes/s", "cores": os.cpu_count(), "kind": "port",
+          "sample": f"{scenes} scenes x {OBJS} objects x {PTS} pts per step (of {SCENES}), full fwd+bwd+AdamW step in fp32 on "
+                    "CPU: sceneverse_b200 host modules + oracle/pointops_ref.c as the point-op `_ext`, torch threads = all cores"}
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": val, "unit": "scenes/s", "n_gpus": 0, "steps": steps,
+                      "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+                      "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "cpu_baseline": cb,
+                      "e2e": {"value": val, "unit": "scenes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def kernel_rooflines(torch, device):
+    """The two gated kernels timed in isolation (CUDA events on the current stream, inputs rotated beyond L2)."""
+    from sceneverse_b200 import _lib, synthetic, weights
+    from sceneverse_b200.modules.pointnet import GPS_SPEC, PointNetPP
+    from sceneverse_b200.pointnet2 import _ext
+    hbm, tfl, src = peaks()
+    B = SCENES * OBJS
+    base = synthetic.object_batch(5, 512, PTS, 0.3)
+    xs = [torch.from_numpy(np.ascontiguousarray(np.tile(base, (B // 512, 1, 1))[np.random.default_rng(i).permutation(B)]))
+          .to(device) for i in range(3)]
+    xyzs = [x[..., :3].contiguous() for x in xs]
+
+    def timed(fn, n=20):
+        for i in range(5):
+            fn(i)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(n):
+            fn(i)
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n
+
+    t_s = timed(lambda i: _ext.fps_ballquery(xyzs[i % 3], NPOINT, RADIUS, NSAMPLE))
+    ach = ALG_BYTES_PER_CLOUD * B / (t_s * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    tj = json.load(open(tp)) if os.path.exists(tp) else {}
+    rp = {"bound": "hbm", "kernel": "sa_sample_kernel<32> (FPS + ball query, one warp per cloud)", "ms": t_s,
+          "mpts_per_s": B * PTS / (t_s * 1e-3) / 1e6, "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+          "traffic": tj.get("sa_sample_kernel_dram_bytes_per_launch", traffic), "algorithmic_bytes_per_launch": ALG_BYTES_PER_CLOUD * B,
+          "peak_source": src, "note": "binding bound is fp32 instruction issue, not HBM (DESIGN.md)"}
+    net = PointNetPP(**GPS_SPEC).eval()
+    net.load_state_dict(weights.synthetic_state_dict(net, 0))
+    net = net.to(device)
+    pk = net._pack()
+    lib = _lib.gps()
+    st = torch.cuda.current_stream().cuda_stream
+    outs = [_ext.sa_sample2(xyz, 32, 0.2, 32, 16, 0.4, 32) for xyz in xyzs]
+    feat1 = [torch.empty((B, 32, 128), dtype=torch.bfloat16, device=device) for _ in range(3)]
+    feat2 = torch.empty((B, 16, 256), dtype=torch.bfloat16, device=device)
+    for i in range(3):
+        _lib.check(lib, lib.sv_sa1_mlp_bf16(xs[i].data_ptr(), outs[i][1].data_ptr(), outs[i][2].data_ptr(),
+                                            pk["sa1"].data_ptr(), B, PTS, 32, feat1[i].data_ptr(), st), "sa1")
+
+    def sa2(i):
+        o = outs[i % 3]
+        _lib.check(lib, lib.sv_sa2_mlp_bf16(o[1].data_ptr(), feat1[i % 3].data_ptr(), o[4].data_ptr(), o[5].data_ptr(),
+                                            pk["sa2"].data_ptr(), B, 32, 32, feat2.data_ptr(), st), "sa2")
+    t_m = timed(sa2)
+    ach_t = SA2_FLOPS_PER_CLOUD * B / (t_m * 1e-3) / 1e12
+    rt = {"bound": "tensor", "kernel": "sa_mlp_kernel<SA2> (gather + 3 tcgen05 GEMMs + max, 131->128->128->256)", "ms": t_m,
+          "achieved": ach_t, "peak": tfl, "unit": "TFLOP/s", "frac": ach_t / tfl,
+          "traffic": tj.get("sa2_mlp_kernel_dram_bytes_per_launch"), "algorithmic_flops_per_launch": SA2_FLOPS_PER_CLOUD * B,
+          "peak_source": src}
+    return rt, rp
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="gps_pretrain", choices=["gps_pretrain", "pointops_sa1"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kernel-rooflines", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-
-    config = {"workload": "pointops_sa1", "scenes_per_gpu": SCENES, "objects_per_scene": OBJS, "points": PTS,
-              "clouds_per_gpu": SCENES * OBJS, "npoint": NPOINT, "radius": RADIUS, "nsample": NSAMPLE,
-              "l2": "inputs rotated over 3 device buffers (189 MB > 126 MB L2)", "parallelism": f"dp{args.gpus}"}
+    warmup = max(args.warmup, 3)
+    config = {"workload": args.workload, "scenes_per_gpu": SCENES, "objects_per_scene": OBJS, "points": PTS,
+              "txt_len": TXT, "scene_txt_len": SCENE_TXT, "global_batch": SCENES * max(world, 1),
+              "losses": ["lm_cls_loss", "TextObjWithinBatch", "TextObjBetweenBatch", "TextSceneBetweenBatch"],
+              "optimizer": "AdamW + clip 5.0 + warmup-cosine", "backbone": "PointNet++ frozen (all_pretrain.yaml)",
+              "l2": "3 distinct input batches rotated (3 x 126 MB of points > 126 MB L2)", "parallelism": f"dp{world}"}
 
     if args.impl == "reference":
-        if rank != 0:
-            return 0
-        steps = max(1, min(args.steps, 5))
-        mpts, dt, cb = cpu_reference_arm(steps, args.warmup)
-        print(json.dumps({"impl": "reference", "metric": "FPS+ball_query Mpts/s (GPS set-abstraction front, model shape)",
-                          "value": mpts, "unit": "Mpts/s", "n_gpus": 0, "steps": steps, "warmup": min(args.warmup, 1),
-                          "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                          "dtype": "f32", "data": "synthetic", "config": config, "cpu_baseline": cb,
-                          "e2e": {"value": mpts, "unit": "Mpts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        if rank == 0:
+            run_reference(args, config)
         return 0
 
     import torch
     import torch.distributed as dist
-    from sceneverse_b200 import _lib
-    from sceneverse_b200.pointnet2 import _ext
-
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    from sceneverse_b200 import _lib, model as M, train, weights
+    from sceneverse_b200.pointnet2 import _ext
     torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    n_clouds = SCENES * OBJS
-    NBUF = 3
-    host = [torch.from_numpy(make_clouds(42 + rank + 100 * i, n_clouds)).pin_memory() for i in range(NBUF)]
-    dev_in = [h.cuda() for h in host]
+        dist.init_process_group("nccl", device_id=device)
     stream = torch.cuda.current_stream()
 
-    def step_resident(i):
-        return _ext.fps_ballquery(dev_in[i % NBUF], NPOINT, RADIUS, NSAMPLE)  # -> sv_sa_sample_f32
+    if args.workload == "pointops_sa1":
+        rt, rp = kernel_rooflines(torch, device)
+        if rank == 0:
+            print(json.dumps({"metric": "FPS+ball_query Mpts/s (model shape)", "value": rp["mpts_per_s"] * world, "unit": "Mpts/s",
+                              "n_gpus": world, "steps": 20, "warmup": 5, "ms_per_step": rp["ms"], "higher_is_better": True,
+                              "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                              "roofline": rp, "gpu_launches": 20}))
+        return 0
 
-    h_fi = torch.empty((n_clouds, NPOINT), dtype=torch.int32).pin_memory()
-    h_bi = torch.empty((n_clouds, NPOINT, NSAMPLE), dtype=torch.int32).pin_memory()
-    d_x = torch.empty_like(dev_in[0])
+    NBUF = 3
+    np_batches = make_scene_batches(NBUF, SCENES, 42 + rank)
+    pinned = [{k: torch.from_numpy(v).pin_memory() for k, v in b.items()} for b in np_batches]
+    resident = [{k: v.to(device) for k, v in p.items()} for p in pinned]
+    h2d_bytes = sum(v.numel() * v.element_size() for v in pinned[0].values())
+    tf = weights.synthetic_tensor("text_features", (607, 768))
+    ps = train.PretrainStep(M.pretrain_config(world, text_features=tf), device, dtype=torch.bfloat16, seed=1234)
+    host_loss = torch.zeros((), dtype=torch.float32).pin_memory()
+
+    def step_resident(i):
+        return ps.step(dict(resident[i % NBUF]))
 
     def step_e2e(i):
-        d_x.copy_(host[i % NBUF], non_blocking=True)
-        fi, nx, bi = _ext.fps_ballquery(d_x, NPOINT, RADIUS, NSAMPLE)
-        h_fi.copy_(fi, non_blocking=True)
-        h_bi.copy_(bi, non_blocking=True)
+        batch = {k: v.to(device, non_blocking=True) for k, v in pinned[i % NBUF].items()}
+        loss = ps.step(batch)
+        host_loss.copy_(loss.float(), non_blocking=True)
+        return loss
 
-    def timed(fn, steps, warmup):
-        for i in range(warmup):
+    def timed(fn, steps, warm):
+        for i in range(warm):
             fn(i)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = _lib.launch_count()
-        ev[0].record(stream)
+        e0.record(stream)
+        last = None
         for i in range(steps):
-            fn(i)
-            ev[i + 1].record(stream)
+            last = fn(i)
+        e1.record(stream)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         launches = _lib.launch_count() - l0
-        total_ms = ev[0].elapsed_time(ev[-1])
-        per = [ev[i].elapsed_time(ev[i + 1]) for i in range(steps)]
-        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+        t = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), per, launches
+        return float(t.item()), launches, float(last)
 
     with ClockSampler(local_rank) as cs:
-        total_ms, per, launches = timed(step_resident, args.steps, max(args.warmup, 3))
-        e2e_ms, _, _ = timed(step_e2e, args.steps, max(args.warmup, 3))
+        total_ms, launches, loss = timed(step_resident, args.steps, warmup)
+        e2e_ms, _, _ = timed(step_e2e, args.steps, warmup)
     clocks = cs.summary()
-
     ms_per_step = total_ms / args.steps
-    mpts = world * n_clouds * PTS / (ms_per_step * 1e-3) / 1e6
-    e2e_mpts = world * n_clouds * PTS / (e2e_ms / args.steps * 1e-3) / 1e6
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return 0
-
-    peak, peak_src = measured_peaks()
-    kern_ms = float(np.mean(per))  # one kernel per step: the CUDA-event step time is the launch duration
-    achieved = ALG_BYTES_PER_CLOUD * n_clouds / (kern_ms * 1e-3) / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
-        traffic = json.load(open(tp)).get("sa_sample_kernel_dram_bytes_per_launch")
-    out = {
-        "metric": "FPS+ball_query Mpts/s (GPS set-abstraction front, model shape)",
-        "value": mpts, "unit": "Mpts/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": config,
-        "scenes_per_s": world * SCENES / (ms_per_step * 1e-3),
-        "roofline": {"bound": "hbm", "kernel": "sa_sample_kernel<32> (FPS + ball query, one warp per cloud)", "achieved": achieved,
-                     "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": ALG_BYTES_PER_CLOUD * n_clouds,
-                     "note": "binding bound is fp32 issue rate, not HBM (DESIGN.md §roofline)"},
-        "e2e": {"value": e2e_mpts, "unit": "Mpts/s", "h2d_bytes_per_step": n_clouds * PTS * 12,
-                "d2h_bytes_per_step": n_clouds * NPOINT * 4 * (1 + NSAMPLE)},
-        "gpu_launches": int(launches), "clocks": clocks,
-    }
-    if not args.no_cpu_baseline:
-        _, _, cb = cpu_reference_arm(2, 1)
-        out["cpu_baseline"] = cb
-    print(json.dumps(out))
+    value = world * SCENES / (ms_per_step * 1e-3)
+    e2e_value = world * SCENES / (e2e_ms / args.steps * 1e-3)
+    rt = rp = None
+    if rank == 0 and not args.no_kernel_rooflines:
+        rt, rp = kernel_rooflines(torch, device)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+    if rank != 0:
+        return 0
+    from sceneverse_b200 import ops
+    out = {"metric": METRIC, "value": value, "unit": "scenes/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
+           "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+           "data": "synthetic", "config": config, "final_loss": loss,
+           "e2e": {"value": e2e_value, "unit": "scenes/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
+           "gpu_launches": int(launches), "clocks": clocks,
+           "native_kernels_in_step": ["sa_sample_kernel (FPS+ball query x2 levels)", "sa_mlp_kernel<SA1>", "sa_mlp_kernel<SA2>"],
+           "library_ops_in_step": [k for k, v in ops.NATIVE.items() if not v] + ["SA3+fc", "BERT-4L (HF)", "AdamW (torch fused)", "NCCL"]}
+    if rt is not None:
+        out["roofline"], out["roofline_pointops"] = rt, rp
+    if not args.no_cpu_baseline:
+        scenes = 2
+        step = cpu_reference_step_fn(scenes)
+        step()
+        t0 = time.perf_counter()
+        step()
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": scenes / dt, "unit": "scenes/s", "cores": os.cpu_count(), "kind": "port",
+                               "sample": f"1 step of {scenes} scenes (of {SCENES}) x {OBJS} x {PTS}, fp32, same modules on CPU "
+                                         "with oracle/pointops_ref.c as `_ext`"}
+    print(json.dumps(out))
     return 0
 
 
