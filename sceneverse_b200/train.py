@@ -54,18 +54,39 @@ class PretrainStep:
             self.optimizer, lambda s: M.warmup_cosine(s, warm, total_steps, minimum_ratio=mr))
         self.grad_norm = self.cfg.solver.get("grad_norm")
         self.ddp = None
-        use_ddp = ddp if ddp is not None else (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1)
-        if use_ddp:
+        self.use_ddp = ddp if ddp is not None else (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1)
+        self.probed = False
+        self.module.train()
+
+    def _probe_unused(self, data_dict):
+        """One local forward/backward to find the parameters this configuration never touches (e.g. the object LM head
+        when `obj_cls_post_logits` is in no loss, all_pretrain.yaml:246-258).  They are frozen once, so DDP can run with
+        find_unused_parameters=False instead of the reference's per-step graph search (trainer/build.py:66)."""
+        self.optimizer.zero_grad(set_to_none=True)
+        with torch.autocast(self.device.type, dtype=self.dtype, enabled=self.dtype != torch.float32):
+            total, _ = self.module(dict(data_dict))
+        total.backward()
+        unused = [n for n, p in self.module.named_parameters() if p.requires_grad and p.grad is None]
+        for n, p in self.module.named_parameters():
+            if p.requires_grad and p.grad is None:
+                p.requires_grad = False
+        self.optimizer.zero_grad(set_to_none=True)
+        for g in self.optimizer.param_groups:
+            g['params'] = [p for p in g['params'] if p.requires_grad]
+        self.unused_parameters = unused
+        if self.use_ddp:
             self.ddp = nn.parallel.DistributedDataParallel(
                 self.module, device_ids=[self.device.index] if self.device.type == "cuda" else None,
                 find_unused_parameters=False, gradient_as_bucket_view=True, bucket_cap_mb=64)
-        self.module.train()
+        self.probed = True
 
     def parameters(self):
         return [p for p in self.module.parameters() if p.requires_grad]
 
     def step(self, data_dict):
         """data_dict: tensors already on self.device. Returns the (detached) total loss tensor — no host sync."""
+        if not self.probed:
+            self._probe_unused(data_dict)
         net = self.ddp if self.ddp is not None else self.module
         self.optimizer.zero_grad(set_to_none=True)
         with torch.autocast(self.device.type, dtype=self.dtype, enabled=self.dtype != torch.float32):
