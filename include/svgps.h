@@ -36,6 +36,15 @@ int sv_sa1_mlp_bf16(const float *pts, const float *new_xyz, const int *ball_idx,
 int sv_sa2_mlp_bf16(const float *xyz, const void *feat, const float *new_xyz, const int *ball_idx, const void *params,
                     int B, int P, int nsample, void *out_feat, void *stream);
 
+/* ---- dense contraction with fused epilogue (tcgen05, TMA, persistent) --------------------------------------------
+ * out[M,N] = epilogue(A[M,K] x B[N,K]^T): A, B bf16 row-major with leading dimensions lda, ldb (elements, % 8 == 0,
+ * K % 8 == 0, 16-byte aligned) — B is the nn.Linear weight layout, so this replaces F.linear / 1x1 Conv2d
+ * (reference call sites: SURVEY.md §2.3).  epilogue: + bias[N] (f32, may be NULL) -> act (0 none, 1 relu, 2 gelu-erf)
+ * -> + residual[M,N] (same dtype / ld as out, may be NULL) -> store bf16 (out_f32 = 0) or f32 (1).
+ * rowmax = 16: instead store max over each group of 16 consecutive rows into out[M/16,N] (PointNet++ SA3 max-pool). */
+int sv_gemm_bf16(const void *A, int lda, const void *B, int ldb, int M, int N, int K, const float *bias, int act,
+                 const void *residual, void *out, int ldo, int out_f32, int rowmax, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -61,6 +61,8 @@ def pointops():
 
 _GPS_SIGS = {
     "sv_tc05_selftest": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
+    "sv_gemm_bf16": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int,
+                     c_int, c_int, c_void_p],
     "sv_sa_mlp_param_bytes": [c_int],
     "sv_sa1_mlp_bf16": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
     "sv_sa2_mlp_bf16": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],

@@ -1,0 +1,288 @@
+// Persistent, warp-specialised tcgen05 GEMM with fused epilogues — the dense-contraction workhorse of the GPS path
+// (every nn.Linear of the attention stack / heads and the SA3 + fc stage of PointNet++; reference: F.linear /
+// 1x1 Conv2d call sites listed in SURVEY.md §2.3).
+//
+//   C[M,N] = epilogue( A[M,K] (bf16, row-major)  x  B[N,K]^T (bf16, row-major = nn.Linear weight layout) )
+//
+// Roles (192 threads): warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator + MMA issuer (one lane),
+// warps 2..5 = epilogue (one thread per accumulator row / TMEM lane).  Operand tiles travel global -> shared by TMA
+// (cp.async.bulk.tensor.2d, one box of [rows x 64 elements] = 128-byte rows, SWIZZLE_128B, read back by the tensor core
+// through a SWIZZLE_128B K-major UMMA descriptor) through a 4-stage mbarrier ring; accumulators are double-buffered
+// in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.  Out-of-bounds rows / columns / K are zero-filled by
+// TMA, the epilogue masks its stores.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "svcommon.h"
+#include "svgps.h"
+#include "tc05.cuh"
+
+namespace {
+
+using namespace tc05;
+
+constexpr int BM = 128, BK = 64, STAGES = 4;
+
+struct GemmArgs {
+  int M, N, K;
+  const float *bias;        // [N] or null
+  const void *residual;     // [M,N] same dtype as out, or null (added after the activation)
+  void *out;                // [M,N] (or [M/rowmax,N] when rowmax > 0)
+  int act;                  // 0 none, 1 relu, 2 gelu(erf)
+  int out_f32;              // 0 bf16, 1 f32
+  int rowmax;               // 0, or 16: max over groups of 16 consecutive rows (SA3 neighbourhood max)
+  int ldo;                  // leading dimension of out / residual (elements)
+};
+
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GemmArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr int A_STAGE = BM * BK * 2, B_STAGE = BN * BK * 2;
+  uint8_t *sA = smem;
+  uint8_t *sB = smem + STAGES * A_STAGE;
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem + STAGES * (A_STAGE + B_STAGE));
+  uint64_t *empty = full + STAGES;
+  uint64_t *acc_full = empty + STAGES;   // [2]
+  uint64_t *acc_empty = acc_full + 2;    // [2]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_m = (g.M + BM - 1) / BM, tiles_n = (g.N + BN - 1) / BN;
+  const int n_tiles = tiles_m * tiles_n;
+  const int k_steps = (g.K + BK - 1) / BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(acc_full + b, 1);
+      mbar_init(acc_empty + b, 128);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<2 * BN>(tmem_slot);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------- TMA producer -------------------------------
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int m0 = (t % tiles_m) * BM, n0 = (t / tiles_m) * BN;
+        for (int ks = 0; ks < k_steps; ++ks, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1u;
+          mbar_wait(empty + s, ph ^ 1u);  // slot free (first pass returns immediately)
+          mbar_expect_tx(full + s, A_STAGE + B_STAGE);
+          const int k0 = ks * BK;
+          tma_load_2d(sA + s * A_STAGE, &mapA, k0, m0, full + s);
+          tma_load_2d(sB + s * B_STAGE, &mapB, k0, n0, full + s);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------- MMA issuer -------------------------------
+    if (lane == 0) {
+      constexpr uint32_t IDESC = make_idesc_bf16(BM, BN);
+      uint32_t it = 0, tl = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tl) {
+        const int b = tl & 1;
+        mbar_wait(acc_empty + b, ((tl >> 1) & 1u) ^ 1u);  // epilogue drained this accumulator
+        fence_after_sync();
+        for (int ks = 0; ks < k_steps; ++ks, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(full + s, (it / STAGES) & 1u);
+          fence_after_sync();
+          const uint32_t a0 = smem_u32(sA + s * A_STAGE), b0 = smem_u32(sB + s * B_STAGE);
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk)
+            mma_bf16(tmem + b * BN, make_desc_sw128(a0 + kk * 32), make_desc_sw128(b0 + kk * 32), IDESC, (ks | kk) != 0);
+          mma_commit(empty + s);  // frees the smem slot when these MMAs retire
+        }
+        mma_commit(acc_full + b);
+      }
+    }
+  } else {
+    // ------------------------------- epilogue (warps 2..5) -------------------------------
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    const int row_in_tile = q * 32 + lane;
+    uint32_t tl = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tl) {
+      const int b = tl & 1;
+      const int m0 = (t % tiles_m) * BM, n0 = (t / tiles_m) * BN;
+      const int row = m0 + row_in_tile;
+      mbar_wait(acc_full + b, (tl >> 1) & 1u);
+      fence_after_sync();
+      const uint32_t taddr = tmem + b * BN + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        float v[32];
+        tmem_ld32(taddr + c0, v);
+        const int col0 = n0 + c0;
+        if (col0 < g.N) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float x = v[i];
+            if (g.bias != nullptr && col0 + i < g.N) x += __ldg(g.bias + col0 + i);  // warp-uniform address: one broadcast
+            if (g.act == 1) x = fmaxf(x, 0.f);
+            else if (g.act == 2) x = gelu_erf(x);
+            v[i] = x;
+          }
+          if (g.rowmax == 16) {
+            // max over the 16 rows of each half-warp (rows are consecutive points of one cloud)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              float x = row < g.M ? v[i] : -INFINITY;
+#pragma unroll
+              for (int o = 8; o > 0; o >>= 1) x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, o));
+              v[i] = x;
+            }
+            if ((lane & 15) == 0 && row < g.M) {
+              const size_t orow = (size_t)(row >> 4);
+              if (g.out_f32) {
+                float *o = reinterpret_cast<float *>(g.out) + orow * g.ldo + col0;
+                for (int i = 0; i < 32 && col0 + i < g.N; ++i) o[i] = v[i];
+              } else {
+                __nv_bfloat16 *o = reinterpret_cast<__nv_bfloat16 *>(g.out) + orow * g.ldo + col0;
+                for (int i = 0; i < 32 && col0 + i < g.N; ++i) o[i] = __float2bfloat16_rn(v[i]);
+              }
+            }
+          } else if (row < g.M) {
+            const bool full32 = col0 + 32 <= g.N;
+            if (g.out_f32) {
+              float *o = reinterpret_cast<float *>(g.out) + (size_t)row * g.ldo + col0;
+              const float *r = g.residual ? reinterpret_cast<const float *>(g.residual) + (size_t)row * g.ldo + col0 : nullptr;
+              if (full32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                  float4 w = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                  if (r) {
+                    const float4 rr = *reinterpret_cast<const float4 *>(r + i);
+                    w.x += rr.x; w.y += rr.y; w.z += rr.z; w.w += rr.w;
+                  }
+                  *reinterpret_cast<float4 *>(o + i) = w;
+                }
+              } else {
+                for (int i = 0; i < 32 && col0 + i < g.N; ++i) o[i] = v[i] + (r ? r[i] : 0.f);
+              }
+            } else {
+              __nv_bfloat16 *o = reinterpret_cast<__nv_bfloat16 *>(g.out) + (size_t)row * g.ldo + col0;
+              const __nv_bfloat16 *r =
+                  g.residual ? reinterpret_cast<const __nv_bfloat16 *>(g.residual) + (size_t)row * g.ldo + col0 : nullptr;
+              if (full32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                  float a[8];
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) a[j] = v[i + j] + (r ? __bfloat162float(r[i + j]) : 0.f);
+                  *reinterpret_cast<uint4 *>(o + i) =
+                      make_uint4(pack_bf16(a[0], a[1]), pack_bf16(a[2], a[3]), pack_bf16(a[4], a[5]), pack_bf16(a[6], a[7]));
+                }
+              } else {
+                for (int i = 0; i < 32 && col0 + i < g.N; ++i)
+                  o[i] = __float2bfloat16_rn(v[i] + (r ? __bfloat162float(r[i]) : 0.f));
+              }
+            }
+          }
+        }
+      }
+      fence_before_sync();
+      mbar_arrive(acc_empty + b);
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<2 * BN>(tmem);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// row-major [rows, K] bf16 with leading dimension ld (elements); box = [box_rows x 64 elements], 128-byte swizzle
+int make_map(CUtensorMap *map, const void *ptr, int rows, int K, int ld, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return SV_ERR_CUDA;
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};  // 64 bf16 = one 128-byte swizzle row
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? SV_OK : SV_ERR_INVALID_ARG;
+}
+
+template <int BN>
+int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mb, const GemmArgs &g, cudaStream_t st) {
+  constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + (2 * STAGES + 4) * 8 + 16;
+  auto kern = gemm_kernel<BN>;
+  static int sms_of_dev[64] = {0};  // also marks "attribute set on this device" (one-time host work per device)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return SV_ERR_INVALID_ARG;
+  if (sms_of_dev[dev] == 0) {
+    int rc = sv::cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (rc) return rc;
+    int n = 148;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    sms_of_dev[dev] = n;
+  }
+  const int sms = sms_of_dev[dev];
+  const int tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN);
+  const int grid = tiles < sms ? tiles : sms;
+  kern<<<grid, 192, smem, st>>>(ma, mb, g);
+  return sv::after_launch();
+}
+
+}  // namespace
+
+extern "C" int sv_gemm_bf16(const void *A, int lda, const void *B, int ldb, int M, int N, int K, const float *bias,
+                            int act, const void *residual, void *out, int ldo, int out_f32, int rowmax, void *stream) {
+  if (M < 0 || N < 0 || K < 0) return SV_ERR_INVALID_ARG;
+  if (M == 0 || N == 0) return SV_OK;
+  if (!A || !B || !out || K < 8 || (K % 8) || (lda % 8) || (ldb % 8) || lda < K || ldb < K) return SV_ERR_INVALID_ARG;
+  if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) return SV_ERR_INVALID_ARG;
+  if (act < 0 || act > 2 || (rowmax != 0 && rowmax != 16) || (rowmax && residual)) return SV_ERR_INVALID_ARG;
+  if (rowmax && (M % 16)) return SV_ERR_INVALID_ARG;
+  GemmArgs g{M, N, K, bias, residual, out, act, out_f32, rowmax, ldo};
+  CUtensorMap ma, mb;
+  const int bn = N > 128 ? 256 : (N > 64 ? 128 : 64);
+  int rc = make_map(&ma, A, M, K, lda, BM);
+  if (rc) return rc;
+  rc = make_map(&mb, B, N, K, ldb, bn);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (bn == 256) return launch_gemm<256>(ma, mb, g, st);
+  if (bn == 128) return launch_gemm<128>(ma, mb, g, st);
+  return launch_gemm<64>(ma, mb, g, st);
+}

@@ -72,6 +72,13 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_b
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
 }
+// K-major SWIZZLE_128B operand (rows of 64 bf16 = 128 B written by TMA with CU_TENSOR_MAP_SWIZZLE_128B, tile base
+// 1024-byte aligned): layout type 2, stride between 8-row groups = 1024 B, leading offset field = 1 (16 B, unused by
+// the hardware for swizzled K-major).  A K=16 step inside the 128-byte row advances the start address by 32 B.
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+         (2ull << 61);
+}
 // instruction descriptor for kind::f16, BF16 x BF16 -> F32, both operands K-major, M = 128
 // (cute::UMMA::InstrDescriptor): c_format[4,6)=1 | a_format[7,10)=1 | b_format[10,13)=1 | n>>3 [17,23) | m>>4 [24,29)
 __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N) {

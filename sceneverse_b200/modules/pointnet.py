@@ -15,7 +15,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from .. import _lib, pointnet2_utils
+from .. import _lib, native, pointnet2_utils
 from ..pointnet2 import _ext
 
 
@@ -150,7 +150,16 @@ class PointNetPP(nn.Module):
                 mlp = self.encoder[lvl].mlps[0]
                 layers = [fold_bn(getattr(mlp, f"layer{j}").conv.weight, getattr(mlp, f"layer{j}").bn.bn) for j in range(3)]
                 packed.append(layers)
-            self._packed = dict(sa1=pack_sa_params(1, packed[0]), sa2=pack_sa_params(2, packed[1]), sa3=packed[2])
+            # SA3 (GroupAll): layer-1 input channels [xyz(3) | feat(256)] re-ordered to [feat(256) | xyz(3) | 0-pad(13)] so
+            # that the bf16 operand rows are 16-byte aligned for TMA (K = 272)
+            (w1, s1), (w2, s2), (w3, s3) = packed[2]
+            w1p = torch.zeros(w1.shape[0], 272, device=w1.device)
+            w1p[:, :256], w1p[:, 256:259] = w1[:, 3:], w1[:, :3]
+            bf = torch.bfloat16
+            sa3 = [(w1p.to(bf).contiguous(), s1.float().contiguous()), (w2.to(bf).contiguous(), s2.float().contiguous()),
+                   (w3.to(bf).contiguous(), s3.float().contiguous())]
+            fc = (self.fc.weight.detach().to(bf).contiguous(), self.fc.bias.detach().float().contiguous())
+            self._packed = dict(sa1=pack_sa_params(1, packed[0]), sa2=pack_sa_params(2, packed[1]), sa3=sa3, fc=fc)
             self._packed_key = key
         return self._packed
 
@@ -186,13 +195,17 @@ class PointNetPP(nn.Module):
         _lib.check(lib, lib.sv_sa2_mlp_bf16(nx1.data_ptr(), feat1.data_ptr(), nx2.data_ptr(), bi2.data_ptr(),
                                             pk["sa2"].data_ptr(), B, 32, sa2.nsample, feat2.data_ptr(), st),
                    "sv_sa2_mlp_bf16")
-        # SA3 (GroupAll over the 16 points, 259->256->512->768, max) + fc.
-        # TODO(round 1, in progress): tcgen05 GEMM-chain kernel; this stage still runs on cuBLAS.
-        x = torch.cat([nx2.to(torch.bfloat16), feat2], dim=2)  # (B,16,259): [xyz | features] = reference channel order
-        for (w, s) in pk["sa3"]:
-            x = torch.relu(F.linear(x, w.to(torch.bfloat16)).float() + s).to(torch.bfloat16)
-        g = x.float().max(dim=1).values
-        out = F.linear(g, self.fc.weight, self.fc.bias)
+        # SA3 (GroupAll over the 16 points: 259->256->512->768, BN folded, ReLU, max over the points) + fc, as four
+        # tcgen05 GEMMs with fused shift/ReLU (and row-group max) epilogues.  xyz is NOT centred here (GroupAll,
+        # pointnet2_utils.py:389-419).
+        x = torch.zeros((B * 16, 272), dtype=torch.bfloat16, device=pts.device)
+        x[:, :256] = feat2.view(B * 16, 256)
+        x[:, 256:259] = nx2.reshape(B * 16, 3).to(torch.bfloat16)
+        (w1, s1), (w2, s2), (w3, s3) = pk["sa3"]
+        x = native.gemm(x, w1, s1, "relu")
+        x = native.gemm(x, w2, s2, "relu")
+        g = native.gemm(x, w3, s3, "relu", rowmax=16)                 # (B,768) bf16: max over the 16 points
+        out = native.gemm(g, pk["fc"][0], pk["fc"][1], out_dtype=torch.float32)
         if return_intermediates:
             return out, dict(fps_idx=fi1, new_xyz=nx1, ball_idx=bi1, fps_idx2=fi2, new_xyz2=nx2, ball_idx2=bi2,
                              feat1=feat1, feat2=feat2)
