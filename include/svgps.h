@@ -45,6 +45,23 @@ int sv_sa2_mlp_bf16(const float *xyz, const void *feat, const float *new_xyz, co
 int sv_gemm_bf16(const void *A, int lda, const void *B, int ldb, int M, int N, int K, const float *bias, int act,
                  const void *residual, void *out, int ldo, int out_f32, int rowmax, void *stream);
 
+/* ---- fused attention forward (tcgen05): O = softmax(Q K^T * scale + spatial gate + key mask) V, head dim 64 ---------
+ * q (B,Lq,*), k/v (B,Lk,*) bf16 with batch strides *_bs and row strides *_rs (elements, % 8 == 0); head h uses columns
+ * [64h, 64h+64).  key_padding_mask (B,Lk) bytes, 1 = ignore (may be NULL).  spatial_w (B,Lq,spatial_heads*6) f32 =
+ * [bias, w1..w5] per head and pairwise_locs (B,Lq,Lk,5) f32 enable the MultiHeadAttentionSpatial 'cond' gate
+ * log(clamp(sigmoid(w . loc + b), 1e-6)) (reference: modules/layers/transformers.py:206-232); NULL = plain attention
+ * (nn.MultiheadAttention core).  Lk <= 160.  out (B,Lq,H*64) bf16. */
+int sv_attention_fwd_bf16(const void *q, long long q_bs, int q_rs, const void *k, long long k_bs, int k_rs,
+                          const void *v, long long v_bs, int v_rs, void *out, long long o_bs, int o_rs,
+                          const unsigned char *key_padding_mask, const float *spatial_w, int spatial_heads,
+                          const float *pairwise_locs, int B, int H, int Lq, int Lk, float scale, void *stream);
+
+/* calc_pairwise_locs, 'center' relation (reference: modules/utils.py:38-87): centers (B,O,*) f32 with row stride
+ * row_stride (>= 3 floats; xyz first) -> out (B,O,O,5) f32 = [dist/max_dist, dz/dist, dist2d/dist, dy/dist2d, dx/dist2d];
+ * dist_norm = 0 keeps the raw distance in slot 0.  eps sits inside the square roots (1e-10 in the reference). */
+int sv_pairwise_locs_f32(const float *centers, int row_stride, int B, int O, float eps, int dist_norm, float *out,
+                         void *stream);
+
 #ifdef __cplusplus
 }
 #endif

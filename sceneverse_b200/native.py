@@ -27,3 +27,28 @@ def gemm(a, w, bias=None, act=None, residual=None, out_dtype=torch.bfloat16, row
                               torch.cuda.current_stream(a.device).cuda_stream)
     _lib.check(lib, st, "sv_gemm_bf16")
     return out
+
+
+def attention(q, k, v, num_heads, key_padding_mask=None, spatial_w=None, spatial_heads=0, pairwise_locs=None):
+    """Fused attention forward: q (B,Lq,E), k/v (B,Lk,E) bf16 (views with a contiguous last dim are fine), head dim 64.
+    key_padding_mask (B,Lk) bool, True = ignore.  spatial_w (B,Lq,spatial_heads*6) + pairwise_locs (B,Lq,Lk,5) switch on the
+    MultiHeadAttentionSpatial 'cond' gate.  Returns (B,Lq,E) bf16."""
+    B, Lq, E = q.shape
+    Lk = k.shape[1]
+    assert E == num_heads * 64 and q.dtype == k.dtype == v.dtype == torch.bfloat16
+    assert q.stride(2) == 1 and k.stride(2) == 1 and v.stride(2) == 1
+    out = torch.empty((B, Lq, E), dtype=torch.bfloat16, device=q.device)
+    kpm = key_padding_mask.to(torch.uint8).contiguous() if key_padding_mask is not None else None
+    sw = locs = None
+    if spatial_w is not None:
+        sw = spatial_w.float().contiguous()
+        locs = pairwise_locs.float().contiguous()
+    lib = _lib.gps()
+    with torch.cuda.device(q.device):
+        st = lib.sv_attention_fwd_bf16(
+            q.data_ptr(), q.stride(0), q.stride(1), k.data_ptr(), k.stride(0), k.stride(1), v.data_ptr(), v.stride(0),
+            v.stride(1), out.data_ptr(), out.stride(0), out.stride(1), kpm.data_ptr() if kpm is not None else None,
+            sw.data_ptr() if sw is not None else None, int(spatial_heads), locs.data_ptr() if locs is not None else None,
+            B, num_heads, Lq, Lk, 0.125, torch.cuda.current_stream(q.device).cuda_stream)
+    _lib.check(lib, st, "sv_attention_fwd_bf16")
+    return out

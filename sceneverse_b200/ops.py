@@ -8,7 +8,36 @@ import math
 import torch
 import torch.nn.functional as F
 
-NATIVE = {"linear": False, "attention": False, "spatial_attention": False, "calc_pairwise_locs": False}
+NATIVE = {"linear": False,              # plain GEMM -> cuBLAS (library GEMM); fused GEMMs (SA3, fc) use native.gemm
+          "attention": "eval",          # nn.MultiheadAttention core: native tcgen05 kernel when no attention dropout is needed
+          "spatial_attention": True,    # MultiHeadAttentionSpatial core: native tcgen05 forward (+ recompute backward)
+          "calc_pairwise_locs": True}
+
+
+def _native_ok(*tensors):
+    return all(t.is_cuda and t.dtype == torch.bfloat16 for t in tensors)
+
+
+class _SpatialAttentionFn(torch.autograd.Function):
+    """Native forward; the backward recomputes the (small) attention in torch from the saved inputs."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, sw, locs, kpm, n_head, spatial_n_head):
+        from . import native
+        ctx.save_for_backward(q, k, v, sw, locs, kpm)
+        ctx.heads = (n_head, spatial_n_head)
+        return native.attention(q, k, v, n_head, key_padding_mask=kpm, spatial_w=sw, spatial_heads=spatial_n_head,
+                                pairwise_locs=locs)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        q, k, v, sw, locs, kpm = ctx.saved_tensors
+        n_head, spatial_n_head = ctx.heads
+        with torch.enable_grad():
+            qq, kk, vv, ss = (t.detach().float().requires_grad_(True) for t in (q, k, v, sw))
+            out, _ = _spatial_attention_torch(qq, kk, vv, ss, locs, n_head, spatial_n_head, kpm)
+            gq, gk, gv, gs = torch.autograd.grad(out, (qq, kk, vv, ss), grad_out.float())
+        return gq.to(q.dtype), gk.to(k.dtype), gv.to(v.dtype), gs.to(sw.dtype), None, None, None, None
 
 
 def linear(x, weight, bias=None, activation=None):
@@ -28,6 +57,18 @@ def calc_pairwise_locs(obj_centers, obj_whls, eps=1e-10, pairwise_rel_type='cent
     [dist/max_dist, dz/dist, dist2d/dist, dy/dist2d, dx/dist2d]; the max-distance normaliser includes padded objects."""
     if pairwise_rel_type != 'center':
         raise NotImplementedError(pairwise_rel_type)
+    if obj_centers.is_cuda and obj_centers.dtype == torch.float32 and spatial_dim == 5 and not obj_centers.requires_grad \
+            and obj_centers.stride(2) == 1 and obj_centers.stride(0) == obj_centers.size(1) * obj_centers.stride(1):
+        from . import _lib
+        B, O, _ = obj_centers.shape
+        out = torch.empty((B, O, O, 5), dtype=torch.float32, device=obj_centers.device)
+        lib = _lib.gps()
+        with torch.cuda.device(obj_centers.device):
+            st = lib.sv_pairwise_locs_f32(obj_centers.data_ptr(), obj_centers.stride(1), B, O, float(eps),
+                                          1 if spatial_dist_norm else 0, out.data_ptr(),
+                                          torch.cuda.current_stream(obj_centers.device).cuda_stream)
+        _lib.check(lib, st, "sv_pairwise_locs_f32")
+        return out
     d = obj_centers[:, :, None, :] - obj_centers[:, None, :, :]
     dist = torch.sqrt((d ** 2).sum(3) + eps)
     if spatial_dist_norm:
@@ -47,6 +88,10 @@ def attention(q, k, v, num_heads, key_padding_mask=None, dropout_p=0.0):
     key_padding_mask (B,Lk) bool, True = ignore (nn.MultiheadAttention convention)."""
     B, Lq, E = q.shape
     Lk, hd = k.shape[1], E // num_heads
+    if (dropout_p == 0.0 and hd == 64 and Lk <= 160 and _native_ok(q, k, v)
+            and not (torch.is_grad_enabled() and (q.requires_grad or k.requires_grad or v.requires_grad))):
+        from . import native
+        return native.attention(q, k, v, num_heads, key_padding_mask=key_padding_mask)
     qh = q.view(B, Lq, num_heads, hd).transpose(1, 2)
     kh = k.view(B, Lk, num_heads, hd).transpose(1, 2)
     vh = v.view(B, Lk, num_heads, hd).transpose(1, 2)
@@ -58,6 +103,16 @@ def attention(q, k, v, num_heads, key_padding_mask=None, dropout_p=0.0):
 
 
 def spatial_attention(q, k, v, spatial_weights, pairwise_locs, n_head, spatial_n_head, key_padding_mask=None):
+    """Dispatch: bf16 CUDA tensors with head dim 64 -> fused tcgen05 kernel (attention map not returned: every reference
+    caller discards it); anything else -> the torch formulation below."""
+    if _native_ok(q, k, v) and q.shape[-1] // n_head == 64 and k.shape[1] <= 160:
+        out = _SpatialAttentionFn.apply(q, k, v, spatial_weights.float(), pairwise_locs.float(), key_padding_mask,
+                                        n_head, spatial_n_head)
+        return out, None
+    return _spatial_attention_torch(q, k, v, spatial_weights, pairwise_locs, n_head, spatial_n_head, key_padding_mask)
+
+
+def _spatial_attention_torch(q, k, v, spatial_weights, pairwise_locs, n_head, spatial_n_head, key_padding_mask=None):
     """Core of MultiHeadAttentionSpatial 'cond' (transformers.py:188-237):
     softmax(log(clamp(sigmoid(w . loc + b), 1e-6)) + q k^T / sqrt(dh)) v, masked keys excluded.
     q,k,v (B,L,E) already projected; spatial_weights (B,L,spatial_n_head*(d+1)), per head [bias, w_1..w_d];

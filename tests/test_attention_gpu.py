@@ -1,0 +1,82 @@
+"""Fused tcgen05 attention forward vs the reference formulas (ops.attention / ops.spatial_attention in fp32 torch)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def rand(*shape, seed=0, scale=1.0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return torch.randn(*shape, device="cuda", generator=g) * scale
+
+
+@pytest.mark.parametrize("Lq,Lk", [(80, 80), (130, 130), (80, 50), (50, 80), (50, 50), (32, 32), (1, 7), (129, 160)])
+def test_plain_attention(Lq, Lk):
+    from sceneverse_b200 import native, ops
+    B, H, E = 3, 12, 768
+    q, k, v = rand(B, Lq, E, seed=1), rand(B, Lk, E, seed=2), rand(B, Lk, E, seed=3)
+    mask = torch.zeros(B, Lk, dtype=torch.bool, device="cuda")
+    mask[1, Lk // 2:] = True
+    mask[2, -1] = True
+    qb, kb, vb = q.bfloat16(), k.bfloat16(), v.bfloat16()
+    got = native.attention(qb, kb, vb, H, key_padding_mask=mask).float()
+    want = ops.attention(qb.float(), kb.float(), vb.float(), H, key_padding_mask=mask)
+    err = (got - want).abs().max().item() / want.abs().max().item()
+    assert err < 2e-2, err
+
+
+def test_packed_qkv_views():
+    from sceneverse_b200 import native, ops
+    B, L, H, E = 2, 130, 12, 768
+    qkv = rand(B, L, 3 * E, seed=5).bfloat16()
+    q, k, v = qkv.split(E, dim=-1)  # strided views, as produced by the packed in-projection
+    got = native.attention(q, k, v, H).float()
+    want = ops.attention(q.float(), k.float(), v.float(), H)
+    assert (got - want).abs().max().item() / want.abs().max().item() < 2e-2
+
+
+@pytest.mark.parametrize("L,spatial_heads", [(80, 12), (32, 12), (80, 1)])
+def test_spatial_attention(L, spatial_heads):
+    from sceneverse_b200 import native, ops
+    B, H, E = 4, 12, 768
+    q, k, v = rand(B, L, E, seed=1).bfloat16(), rand(B, L, E, seed=2).bfloat16(), rand(B, L, E, seed=3).bfloat16()
+    sw = rand(B, L, spatial_heads * 6, seed=4, scale=2.0)
+    centers = rand(B, L, 3, seed=6, scale=2.0)
+    locs = ops.calc_pairwise_locs(centers, None)
+    mask = torch.zeros(B, L, dtype=torch.bool, device="cuda")
+    mask[0, L - 7:] = True
+    mask[3, 5:] = True
+    got = native.attention(q, k, v, H, key_padding_mask=mask, spatial_w=sw, spatial_heads=spatial_heads,
+                           pairwise_locs=locs).float()
+    want, _ = ops._spatial_attention_torch(q.float(), k.float(), v.float(), sw, locs, H, spatial_heads, key_padding_mask=mask)
+    err = (got - want).abs().max().item() / want.abs().max().item()
+    assert err < 2e-2, err
+
+
+def test_spatial_attention_backward_matches_torch():
+    from sceneverse_b200 import ops
+    B, L, H, E = 2, 80, 12, 768
+    q, k, v = (rand(B, L, E, seed=s).bfloat16().requires_grad_(True) for s in (1, 2, 3))
+    sw = rand(B, L, 72, seed=4).requires_grad_(True)
+    locs = ops.calc_pairwise_locs(rand(B, L, 3, seed=6, scale=2.0), None)
+    out, attn = ops.spatial_attention(q, k, v, sw, locs, H, H)
+    assert attn is None and out.dtype == torch.bfloat16
+    out.float().square().sum().backward()
+    g_native = [t.grad.clone() for t in (q, k, v, sw)]
+    for t in (q, k, v, sw):
+        t.grad = None
+    out2, _ = ops._spatial_attention_torch(q.float(), k.float(), v.float(), sw, locs, H, H)
+    out2.float().square().sum().backward()
+    for a, b in zip(g_native, (q.grad, k.grad, v.grad, sw.grad)):
+        assert (a.float() - b.float()).abs().max().item() <= 5e-2 * b.float().abs().max().item() + 1e-6
+
+
+def test_pairwise_locs_kernel_matches_torch():
+    from sceneverse_b200 import ops
+    locs6 = rand(5, 80, 6, seed=9, scale=3.0)
+    locs6[2, 40:] = 0.0  # padded objects sit at the origin and take part in the max distance
+    got = ops.calc_pairwise_locs(locs6[:, :, :3], locs6[:, :, 3:])            # strided view -> native kernel
+    c = locs6[:, :, :3].cpu()
+    want = ops.calc_pairwise_locs(c, None)                                     # torch formulation on CPU
+    assert got.shape == (5, 80, 80, 5)
+    assert torch.allclose(got.cpu(), want, rtol=2e-5, atol=2e-6)
