@@ -150,3 +150,32 @@ def warmup_cosine(step, warmup_step, total_step, minimum_ratio=1e-5):
     if step <= warmup_step and warmup_step > 0:
         return step / warmup_step
     return max(0.5 * (1 + math.cos((step - warmup_step) / max(total_step - warmup_step, 1) * math.pi)), minimum_ratio)
+
+
+class ObjCls(nn.Module):
+    """Object-level pre-training model (reference: model/objcls.py:16-98), `model_name='pointnet++'`, open-vocabulary
+    head against the 607 frozen text embeddings, bert language type (768-d).  PointNet++ is trainable here with
+    train-mode BatchNorm (SyncBatchNorm when num_gpu > 1, objcls.py:33-34), so it runs the generic operator sequence on
+    the native point ops — the one shipped path that needs `group_points_grad`."""
+
+    def __init__(self, cfg, text_embeds=None):
+        super().__init__()
+        from .modules.pointnet import GPS_SPEC, PointNetPP
+        self.cfg = cfg = to_cfg(cfg)
+        self.point_feature_extractor = PointNetPP(**GPS_SPEC)
+        if cfg.num_gpu > 1:
+            self.point_feature_extractor = torch.nn.SyncBatchNorm.convert_sync_batchnorm(self.point_feature_extractor)
+        self.register_buffer("text_embeds", text_embeds.float())
+        self.dropout = nn.Dropout(0.1)
+
+    def forward(self, data_dict):
+        obj_pcds = data_dict["obj_fts"]
+        B, O = obj_pcds.shape[:2]
+        emb = self.point_feature_extractor(obj_pcds.reshape(B * O, *obj_pcds.shape[2:]).float())
+        emb = self.dropout(emb)
+        data_dict["obj_logits"] = (emb @ self.text_embeds.t().to(emb.dtype)).view(B, O, -1)
+        return data_dict
+
+    def get_opt_params(self):
+        return [{"params": list(self.parameters()), "weight_decay": self.cfg.solver.get("weight_decay", 0.0),
+                 "lr": self.cfg.solver.lr}]

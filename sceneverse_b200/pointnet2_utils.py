@@ -37,7 +37,11 @@ class _Gather(Function):
         return _ext.gather_points_grad(grad_out.contiguous(), ctx.idx, ctx.n), None
 
 
-gather_operation = _Gather.apply
+def gather_operation(features, idx):
+    """pointnet2_utils.py:80-114 (fp32 kernel; other dtypes are widened)."""
+    if features.dtype != torch.float32:
+        features = features.float()
+    return _Gather.apply(features.contiguous(), idx)
 
 
 class _ThreeNN(Function):
@@ -81,7 +85,12 @@ class _Grouping(Function):
         return _ext.group_points_grad(grad_out.contiguous(), ctx.idx, ctx.n), None
 
 
-grouping_operation = _Grouping.apply
+def grouping_operation(features, idx):
+    """pointnet2_utils.py:206-254.  The native kernel is fp32-only like the reference's (utils.h:21-25); reduced-precision
+    features (bf16 autocast with a trainable backbone, where the reference itself would assert) are widened first."""
+    if features.dtype != torch.float32:
+        features = features.float()
+    return _Grouping.apply(features.contiguous(), idx)
 
 
 class _BallQuery(Function):

@@ -107,3 +107,58 @@ def test_sa_kernels_against_bf16_emulation():
     want2 = emulate(rows2, net.encoder[1].mlps[0])
     got2 = it["feat2"].float()
     assert (got2 - want2).abs().max().item() <= 2e-2 * want2.abs().max().item()
+
+
+@pytest.mark.gpu
+def test_objcls_step_trains_pointnet_through_native_grads():
+    """BASELINE.json configs[1]: 64 objects x 1024 points, PointNet++ trainable (train-mode BN), bf16 autocast,
+    607-way open-vocabulary CE with label smoothing: one optimisation step must produce finite gradients for every
+    PointNet++ parameter through group_points_grad, and match the same step computed with torch gathers."""
+    from sceneverse_b200 import model as M
+    from sceneverse_b200.modules import losses
+    d = synthetic.scene_batch(5, B=1, O=64, P=1024, all_valid=True)
+    batch = {k: torch.from_numpy(v).cuda() for k, v in d.items()}
+    tf = weights.synthetic_tensor("text_features", (607, 768)).cuda()
+    net = M.ObjCls({"num_gpu": 1, "solver": {"lr": 1e-3}}, text_embeds=tf).cuda().train()
+    net.point_feature_extractor.load_state_dict(weights.synthetic_state_dict(net.point_feature_extractor, 0))
+    net.dropout.p = 0.0
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = net(dict(batch))
+        loss = losses.obj_cls_loss(out)
+    loss.backward()
+    grads = {n: p.grad for n, p in net.named_parameters()}
+    assert all(g is not None and torch.isfinite(g).all() for g in grads.values())
+    assert float(grads["point_feature_extractor.encoder.0.mlps.0.layer0.conv.weight"].abs().sum()) > 0
+    # same computation with torch.gather instead of the native group/gather kernels (identical indices)
+    pn = net.point_feature_extractor
+    x = batch["obj_fts"].view(64, 1024, 6).float()
+    xyz, feats = x[..., :3].contiguous(), x[..., 3:].transpose(1, 2).contiguous()
+    for p in net.parameters():
+        p.grad = None
+    from sceneverse_b200.pointnet2 import _ext
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        for sa in pn.encoder:
+            if sa.npoint is not None:
+                fi = _ext.furthest_point_sampling(xyz, sa.npoint).long()
+                new_xyz = torch.gather(xyz, 1, fi[..., None].expand(-1, -1, 3))
+                bi = _ext.ball_query(new_xyz.contiguous(), xyz, sa.radius, sa.nsample).long()
+                Bn, npnt, ns = bi.shape
+                gx = torch.gather(xyz[:, None].expand(-1, npnt, -1, -1), 2, bi[..., None].expand(-1, -1, -1, 3))
+                gx = (gx - new_xyz[:, :, None]).permute(0, 3, 1, 2)
+                C = feats.shape[1]
+                gf = torch.gather(feats[:, :, None].expand(-1, -1, npnt, -1), 3, bi[:, None].expand(-1, C, -1, -1))
+                g = torch.cat([gx, gf], 1)
+            else:
+                new_xyz = None
+                g = torch.cat([xyz.transpose(1, 2).unsqueeze(2), feats.unsqueeze(2)], 1)
+            h = sa.mlps[0](g)
+            feats = torch.nn.functional.max_pool2d(h, kernel_size=[1, h.size(3)]).squeeze(-1)
+            xyz = new_xyz
+        emb = pn.fc(feats.view(64, -1))
+        out2 = {"obj_logits": (emb @ tf.t().to(emb.dtype)).view(1, 64, -1), "obj_labels": batch["obj_labels"], "obj_masks": batch["obj_masks"]}
+        loss2 = losses.obj_cls_loss(out2)
+    loss2.backward()
+    assert abs(float(loss) - float(loss2)) < 2e-2 * abs(float(loss2))
+    g1 = grads["point_feature_extractor.encoder.1.mlps.0.layer0.conv.weight"].float()
+    g2 = pn.encoder[1].mlps[0].layer0.conv.weight.grad.float()
+    assert (g1 - g2).abs().max().item() <= 0.1 * g2.abs().max().item() + 1e-6
