@@ -62,6 +62,13 @@ int sv_attention_fwd_bf16(const void *q, long long q_bs, int q_rs, const void *k
 int sv_pairwise_locs_f32(const float *centers, int row_stride, int B, int O, float eps, int dist_norm, float *out,
                          void *stream);
 
+/* Fused softmax cross-entropy, forward + gradient (reference: optim/loss/loss.py:8-9,56-61 — F.cross_entropy with
+ * ignore_index): logits (R,V) bf16 (is_bf16 = 1) or f32, rows row_stride elements apart; labels (R) int64.
+ * loss_rows[r] = logsumexp(row) - row[label] (0 for ignored rows); grad_logits (R,V, contiguous, same dtype, may be NULL)
+ * = softmax(row) - onehot(label) (zero rows for ignored labels).  The caller divides by the number of valid rows. */
+int sv_cross_entropy_fwd_bwd(const void *logits, long long row_stride, int is_bf16, const long long *labels, int R, int V,
+                             long long ignore_index, float *loss_rows, void *grad_logits, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,6 +6,7 @@ import torch.distributed as dist
 import torch.nn.functional as F
 from torch import nn
 
+from .. import ops
 from .registry import LOSS_REGISTRY
 
 
@@ -28,13 +29,14 @@ def all_gather(tensors):
 
 
 def og3d_loss(data_dict):
-    return F.cross_entropy(data_dict["og3d_logits"], data_dict["tgt_object_id"].squeeze(1))
+    return ops.cross_entropy(data_dict["og3d_logits"], data_dict["tgt_object_id"].squeeze(1))
 
 
 def lm_cls_loss(data_dict):
+    """loss.py:56-61: cross-entropy over the vocabulary at the masked positions (label -1 = not supervised)."""
     target = data_dict["masked_lm_labels"]
     target = target.view(-1, target.size(-1)) if target.dim() == 3 else target
-    return F.cross_entropy(data_dict["txt_lm_cls_logits"].permute(0, 2, 1), target, ignore_index=-1)
+    return ops.cross_entropy(data_dict["txt_lm_cls_logits"], target, ignore_index=-1)
 
 
 def obj_cls_loss(data_dict, smoothing=0.3):

@@ -11,7 +11,8 @@ import torch.nn.functional as F
 NATIVE = {"linear": False,              # plain GEMM -> cuBLAS (library GEMM); fused GEMMs (SA3, fc) use native.gemm
           "attention": "eval",          # nn.MultiheadAttention core: native tcgen05 kernel when no attention dropout is needed
           "spatial_attention": True,    # MultiHeadAttentionSpatial core: native tcgen05 forward (+ recompute backward)
-          "calc_pairwise_locs": True}
+          "calc_pairwise_locs": True,
+          "cross_entropy": True}        # masked-LM / grounding CE: fused native forward+gradient
 
 
 def _native_ok(*tensors):
@@ -135,3 +136,41 @@ def _spatial_attention_torch(q, k, v, spatial_weights, pairwise_locs, n_head, sp
     fused = torch.softmax(torch.log(torch.clamp(loc, min=1e-6)) + attn, 3)
     out = torch.einsum('hblt,hbtv->hblv', fused, vh).permute(1, 2, 0, 3).reshape(B, L, E)
     return out, fused
+
+
+class _CrossEntropyFn(torch.autograd.Function):
+    """mean cross-entropy over the rows whose label != ignore_index; forward and gradient come from ONE native launch."""
+
+    @staticmethod
+    def forward(ctx, logits2d, labels, ignore_index):
+        from . import _lib
+        R, V = logits2d.shape
+        loss_rows = torch.empty(R, dtype=torch.float32, device=logits2d.device)
+        need_grad = logits2d.requires_grad
+        grad = torch.empty((R, V), dtype=logits2d.dtype, device=logits2d.device) if need_grad else None
+        lib = _lib.gps()
+        with torch.cuda.device(logits2d.device):
+            st = lib.sv_cross_entropy_fwd_bwd(logits2d.data_ptr(), logits2d.stride(0), 1 if logits2d.dtype == torch.bfloat16 else 0,
+                                              labels.data_ptr(), R, V, int(ignore_index), loss_rows.data_ptr(),
+                                              grad.data_ptr() if grad is not None else None,
+                                              torch.cuda.current_stream(logits2d.device).cuda_stream)
+        _lib.check(lib, st, "sv_cross_entropy_fwd_bwd")
+        count = (labels != ignore_index).sum().clamp(min=1).float()
+        ctx.save_for_backward(grad, count)
+        return loss_rows.sum() / count
+
+    @staticmethod
+    def backward(ctx, gout):
+        grad, count = ctx.saved_tensors
+        return grad.mul_((gout / count).to(grad.dtype)), None, None
+
+
+def cross_entropy(logits, labels, ignore_index=-100):
+    """F.cross_entropy(logits.permute(0, 2, 1) / logits, labels, ignore_index=...) with the class dimension LAST in
+    `logits` ((..., V) with (...) matching labels).  CUDA bf16/f32 -> fused native kernel; otherwise torch."""
+    V = logits.shape[-1]
+    if logits.is_cuda and logits.dtype in (torch.bfloat16, torch.float32) and logits.stride(-1) == 1:
+        l2 = logits.reshape(-1, V)
+        if l2.stride(1) == 1:
+            return _CrossEntropyFn.apply(l2, labels.reshape(-1).contiguous(), ignore_index)
+    return F.cross_entropy(logits.reshape(-1, V).float(), labels.reshape(-1), ignore_index=ignore_index)

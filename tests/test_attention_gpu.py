@@ -80,3 +80,30 @@ def test_pairwise_locs_kernel_matches_torch():
     want = ops.calc_pairwise_locs(c, None)                                     # torch formulation on CPU
     assert got.shape == (5, 80, 80, 5)
     assert torch.allclose(got.cpu(), want, rtol=2e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_fused_cross_entropy_matches_torch(dtype):
+    from sceneverse_b200 import ops
+    R, V = 300, 30522
+    logits = (rand(R, V, seed=11) * 3).to(dtype).requires_grad_(True)
+    labels = torch.randint(0, V, (R,), device="cuda")
+    labels[torch.rand(R, device="cuda") < 0.8] = -1
+    labels[0] = 5
+    loss = ops.cross_entropy(logits.view(6, 50, V), labels.view(6, 50), ignore_index=-1)
+    loss.backward()
+    ref_logits = logits.detach().float().requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(ref_logits, labels, ignore_index=-1)
+    ref.backward()
+    assert abs(float(loss) - float(ref)) < (2e-3 if dtype == torch.bfloat16 else 1e-5) * max(1.0, abs(float(ref)))
+    g, gr = logits.grad.float(), ref_logits.grad
+    assert (g - gr).abs().max().item() <= (1e-2 if dtype == torch.bfloat16 else 1e-6) * gr.abs().max().item() + 1e-9
+    # -inf logits (masked objects in og3d) give zero probability, not NaN
+    og = rand(4, 80, seed=12)
+    og[:, 60:] = float("-inf")
+    og.requires_grad_(True)
+    tgt = torch.tensor([[3], [10], [59], [0]], device="cuda")
+    l2 = ops.cross_entropy(og, tgt.squeeze(1))
+    l2.backward()
+    want = torch.nn.functional.cross_entropy(og.detach(), tgt.squeeze(1))
+    assert abs(float(l2) - float(want)) < 1e-5 and torch.isfinite(og.grad).all()
