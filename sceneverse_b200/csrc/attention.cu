@@ -36,9 +36,19 @@ struct AttnArgs {
 
 constexpr int DH = 64;
 
+// gate(j) = log(clamp(sigmoid(w . loc_j + b), 1e-6)) for 4 consecutive keys from 5 float4 of the (Lk,5) row
+struct Gate {
+  float wb, w0, w1, w2, w3, w4;
+  __device__ __forceinline__ float one(float l0, float l1, float l2, float l3, float l4) const {
+    const float z = wb + w0 * l0 + w1 * l1 + w2 * l2 + w3 * l3 + w4 * l4;
+    return __logf(fmaxf(1.0f / (1.0f + __expf(-z)), 1e-6f));
+  }
+};
+
+template <int NCH>  // NCH = NKP / 32 (1..5)
 __global__ void __launch_bounds__(128, 2) attention_fwd_kernel(const AttnArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int NKP = a.NKP;
+  constexpr int NKP = NCH * 32;
   uint8_t *sQ = smem;                          // [128 x 64]   rows = queries, K = dh
   uint8_t *sK = sQ + 128 * DH * 2;             // [NKP x 64]   rows = keys,    K = dh
   uint8_t *sVt = sK + NKP * DH * 2;            // [64 x NKP]   rows = dh,      K = keys
@@ -46,11 +56,8 @@ __global__ void __launch_bounds__(128, 2) attention_fwd_kernel(const AttnArgs a)
   uint64_t *mbar = reinterpret_cast<uint64_t *>(sP + 128 * NKP * 2);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(mbar + 1);
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
-  const int q0 = blockIdx.y * 128;
-  const int qi = q0 + tid;  // this thread's query row
-  const bool qlive = qi < a.Lq;
 
   if (tid == 0) {
     mbar_init(mbar, 1);
@@ -58,160 +65,201 @@ __global__ void __launch_bounds__(128, 2) attention_fwd_kernel(const AttnArgs a)
   }
   if (warp == 0) tmem_alloc<256>(tmem_slot);
 
-  // ---- stage Q, K, V^T -----------------------------------------------------------------------------------------
-  {
-    uint4 row[8];
-    if (qlive) {
-      const uint4 *src = reinterpret_cast<const uint4 *>(a.q + (size_t)b * a.q_bs + (size_t)qi * a.q_rs + h * DH);
-#pragma unroll
-      for (int c = 0; c < 8; ++c) row[c] = __ldg(src + c);
-    } else {
-#pragma unroll
-      for (int c = 0; c < 8; ++c) row[c] = make_uint4(0, 0, 0, 0);
+  // ---- stage K and V^T once per (scene, head) ---------------------------------------------------------------------
+  // thread = (key pair, 8-column chunk): two keys' values of one column are packed into one 32-bit shared store
+  for (int e = tid; e < (NKP / 2) * 8; e += 128) {
+    const int jp = e >> 3, c = e & 7;
+    const int j0 = 2 * jp;
+    uint4 k0 = make_uint4(0, 0, 0, 0), k1 = k0, v0 = k0, v1 = k0;
+    if (j0 < a.Lk) {
+      k0 = __ldg(reinterpret_cast<const uint4 *>(a.k + (size_t)b * a.k_bs + (size_t)j0 * a.k_rs + h * DH) + c);
+      v0 = __ldg(reinterpret_cast<const uint4 *>(a.v + (size_t)b * a.v_bs + (size_t)j0 * a.v_rs + h * DH) + c);
     }
+    if (j0 + 1 < a.Lk) {
+      k1 = __ldg(reinterpret_cast<const uint4 *>(a.k + (size_t)b * a.k_bs + (size_t)(j0 + 1) * a.k_rs + h * DH) + c);
+      v1 = __ldg(reinterpret_cast<const uint4 *>(a.v + (size_t)b * a.v_bs + (size_t)(j0 + 1) * a.v_rs + h * DH) + c);
+    }
+    *reinterpret_cast<uint4 *>(sK + tile_off(NKP, j0, c * 8)) = k0;
+    *reinterpret_cast<uint4 *>(sK + tile_off(NKP, j0 + 1, c * 8)) = k1;
+    const unsigned short *e0 = reinterpret_cast<const unsigned short *>(&v0);
+    const unsigned short *e1 = reinterpret_cast<const unsigned short *>(&v1);
 #pragma unroll
-    for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4 *>(sQ + tile_off(128, tid, c * 8)) = row[c];
+    for (int i = 0; i < 8; ++i)
+      *reinterpret_cast<uint32_t *>(sVt + tile_off(DH, c * 8 + i, j0)) = (uint32_t)e0[i] | ((uint32_t)e1[i] << 16);
   }
-  for (int j = tid; j < NKP; j += 128) {
-    uint4 kr[8], vr[8];
-    if (j < a.Lk) {
-      const uint4 *ks = reinterpret_cast<const uint4 *>(a.k + (size_t)b * a.k_bs + (size_t)j * a.k_rs + h * DH);
-      const uint4 *vs = reinterpret_cast<const uint4 *>(a.v + (size_t)b * a.v_bs + (size_t)j * a.v_rs + h * DH);
+  // key mask as one bit per key (bit set = key takes part), chunk c in kmask[c]
+  uint32_t kmask[NCH];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        kr[c] = __ldg(ks + c);
-        vr[c] = __ldg(vs + c);
-      }
-    } else {
-#pragma unroll
-      for (int c = 0; c < 8; ++c) kr[c] = vr[c] = make_uint4(0, 0, 0, 0);
-    }
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      *reinterpret_cast<uint4 *>(sK + tile_off(NKP, j, c * 8)) = kr[c];
-      const unsigned short *e = reinterpret_cast<const unsigned short *>(&vr[c]);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) *reinterpret_cast<unsigned short *>(sVt + tile_off(DH, c * 8 + i, j)) = e[i];
-    }
+  for (int c = 0; c < NCH; ++c) {
+    const int j = c * 32 + lane;
+    const bool on = j < a.Lk && !(a.kpm && a.kpm[(size_t)b * a.Lk + j]);
+    kmask[c] = __ballot_sync(0xffffffffu, on);
   }
-  fence_proxy_async_smem();
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = *tmem_slot;
   const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
   constexpr uint32_t COL_S = 0, COL_O = 192;  // S: up to 160 columns, O: 64 columns
+  uint32_t phase = 0;
 
-  // ---- S = Q K^T --------------------------------------------------------------------------------------------------
-  if (tid == 0) {
-    const uint32_t idesc = make_idesc_bf16(128, NKP);
-    const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK);
+  for (int q0 = 0; q0 < a.Lq; q0 += 128) {
+    const int qi = q0 + tid;  // this thread's query row
+    const bool qlive = qi < a.Lq;
+    // ---- stage the Q tile ------------------------------------------------------------------------------------------
+    {
+      const uint4 *src = reinterpret_cast<const uint4 *>(a.q + (size_t)b * a.q_bs + (size_t)qi * a.q_rs + h * DH);
 #pragma unroll
-    for (int ks = 0; ks < DH / 16; ++ks)
-      mma_bf16(tmem + COL_S, make_desc(aQ + ks * 2 * 2048, 2048, 128), make_desc(aK + ks * 2 * (NKP * 16), NKP * 16, 128),
-               idesc, ks > 0);
-    mma_commit(mbar);
-  }
-  // spatial gate parameters of this (query, head) while the MMA runs
-  float wb = 0.f, w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f, w4 = 0.f;
-  const float *loc = nullptr;
-  if (a.sw != nullptr && qlive) {
-    const float *w = a.sw + ((size_t)b * a.Lq + qi) * (a.SH * 6) + (a.SH == 1 ? 0 : h) * 6;
-    wb = w[0]; w0 = w[1]; w1 = w[2]; w2 = w[3]; w3 = w[4]; w4 = w[5];
-    loc = a.locs + ((size_t)b * a.Lq + qi) * (size_t)a.Lk * 5;
-  }
-  const unsigned char *kpm = a.kpm ? a.kpm + (size_t)b * a.Lk : nullptr;
-  mbar_wait(mbar, 0);
-  fence_after_sync();
-
-  // ---- softmax over the keys of this thread's query row (two passes over TMEM: max, then exp/sum/store) ---------
-  float mx = -INFINITY;
-  for (int c0 = 0; c0 < NKP; c0 += 32) {
-    float v[32];
-    tmem_ld32(trow + COL_S + c0, v);
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const int j = c0 + i;
-      float x = -INFINITY;
-      if (j < a.Lk && !(kpm && kpm[j])) {
-        x = v[i] * a.scale;
-        if (loc) {
-          const float *l = loc + (size_t)j * 5;
-          const float z = wb + w0 * l[0] + w1 * l[1] + w2 * l[2] + w3 * l[3] + w4 * l[4];
-          const float sg = 1.0f / (1.0f + __expf(-z));
-          x += __logf(fmaxf(sg, 1e-6f));
-        }
-      }
-      mx = fmaxf(mx, x);
+      for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<uint4 *>(sQ + tile_off(128, tid, c * 8)) = qlive ? __ldg(src + c) : make_uint4(0, 0, 0, 0);
     }
-  }
-  float sum = 0.f;
-  for (int c0 = 0; c0 < NKP; c0 += 32) {
-    float v[32];
-    tmem_ld32(trow + COL_S + c0, v);
+    fence_proxy_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    // ---- S = Q K^T --------------------------------------------------------------------------------------------------
+    if (tid == 0) {
+      fence_after_sync();
+      const uint32_t idesc = make_idesc_bf16(128, NKP);
+      const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const int j = c0 + i;
-      float p = 0.f;
-      if (j < a.Lk && !(kpm && kpm[j]) && mx > -INFINITY) {
-        float x = v[i] * a.scale;
-        if (loc) {
-          const float *l = loc + (size_t)j * 5;
-          const float z = wb + w0 * l[0] + w1 * l[1] + w2 * l[2] + w3 * l[3] + w4 * l[4];
-          const float sg = 1.0f / (1.0f + __expf(-z));
-          x += __logf(fmaxf(sg, 1e-6f));
-        }
-        p = __expf(x - mx);
-      }
-      sum += p;
-      v[i] = p;
+      for (int ks = 0; ks < DH / 16; ++ks)
+        mma_bf16(tmem + COL_S, make_desc(aQ + ks * 4096, 2048, 128), make_desc(aK + ks * 2 * (NKP * 16), NKP * 16, 128),
+                 idesc, ks > 0);
+      mma_commit(mbar);
     }
-    // unnormalised probabilities -> bf16 A operand; the 1/sum is applied to the fp32 output row
+    // spatial gate of this (query, head): computed ONCE per key while the MMA runs, kept in registers
+    float gate[NKP];
+    const bool gated = a.sw != nullptr;
+    if (gated) {
 #pragma unroll
-    for (int qd = 0; qd < 4; ++qd) {
-      uint32_t w[4];
-#pragma unroll
-      for (int hh = 0; hh < 4; ++hh) w[hh] = pack_bf16(v[qd * 8 + hh * 2], v[qd * 8 + hh * 2 + 1]);
-      *reinterpret_cast<uint4 *>(sP + tile_off(128, tid, c0 + qd * 8)) = make_uint4(w[0], w[1], w[2], w[3]);
-    }
-  }
-  fence_proxy_async_smem();
-  fence_before_sync();
-  __syncthreads();
-
-  // ---- O = P V -----------------------------------------------------------------------------------------------------
-  if (tid == 0) {
-    fence_after_sync();
-    const uint32_t idesc = make_idesc_bf16(128, DH);
-    const uint32_t aP = smem_u32(sP), aV = smem_u32(sVt);
-    for (int ks = 0; ks < NKP / 16; ++ks)
-      mma_bf16(tmem + COL_O, make_desc(aP + ks * 2 * 2048, 2048, 128), make_desc(aV + ks * 2 * (DH * 16), DH * 16, 128),
-               idesc, ks > 0);
-    mma_commit(mbar);
-  }
-  mbar_wait(mbar, 1);
-  fence_after_sync();
-  {
-    const float inv = sum > 0.f ? 1.0f / sum : 0.f;
-    __nv_bfloat16 *o = a.out + (size_t)b * a.o_bs + (size_t)qi * a.o_rs + h * DH;
-#pragma unroll
-    for (int c0 = 0; c0 < DH; c0 += 32) {
-      float v[32];
-      tmem_ld32(trow + COL_O + c0, v);
+      for (int j = 0; j < NKP; ++j) gate[j] = 0.f;
       if (qlive) {
+        const float *w = a.sw + ((size_t)b * a.Lq + qi) * (a.SH * 6) + (a.SH == 1 ? 0 : h) * 6;
+        const Gate g{w[0], w[1], w[2], w[3], w[4], w[5]};
+        const float *loc = a.locs + ((size_t)b * a.Lq + qi) * (size_t)a.Lk * 5;
+        if ((a.Lk & 3) == 0) {
+          const float4 *l4 = reinterpret_cast<const float4 *>(loc);
 #pragma unroll
-        for (int qd = 0; qd < 4; ++qd) {
-          uint32_t w[4];
+          for (int j = 0; j < NKP; j += 4) {
+            if (j < a.Lk) {
+              const float4 A = __ldg(l4 + (j >> 2) * 5), B2 = __ldg(l4 + (j >> 2) * 5 + 1), C = __ldg(l4 + (j >> 2) * 5 + 2),
+                           D = __ldg(l4 + (j >> 2) * 5 + 3), E = __ldg(l4 + (j >> 2) * 5 + 4);
+              gate[j] = g.one(A.x, A.y, A.z, A.w, B2.x);
+              gate[j + 1] = g.one(B2.y, B2.z, B2.w, C.x, C.y);
+              gate[j + 2] = g.one(C.z, C.w, D.x, D.y, D.z);
+              gate[j + 3] = g.one(D.w, E.x, E.y, E.z, E.w);
+            }
+          }
+        } else {
 #pragma unroll
-          for (int hh = 0; hh < 4; ++hh) w[hh] = pack_bf16(v[qd * 8 + hh * 2] * inv, v[qd * 8 + hh * 2 + 1] * inv);
-          *reinterpret_cast<uint4 *>(o + c0 + qd * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+          for (int j = 0; j < NKP; ++j)
+            if (j < a.Lk) gate[j] = g.one(loc[j * 5], loc[j * 5 + 1], loc[j * 5 + 2], loc[j * 5 + 3], loc[j * 5 + 4]);
         }
       }
     }
+    mbar_wait(mbar, phase);
+    phase ^= 1u;
+    fence_after_sync();
+
+    // ---- softmax over the keys of this thread's query row ----------------------------------------------------------
+    // gated (<= 96 keys in practice): logits cached in `gate`; plain: second TMEM pass instead of 160 registers
+    float mx = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      float v[32];
+      tmem_ld32(trow + COL_S + c * 32, v);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const bool on = (kmask[c] >> i) & 1u;
+        float x = v[i] * a.scale;
+        if (gated) {
+          x += gate[c * 32 + i];
+          gate[c * 32 + i] = on ? x : -INFINITY;
+        }
+        mx = fmaxf(mx, on ? x : -INFINITY);
+      }
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      float v[32];
+      if (!gated) tmem_ld32(trow + COL_S + c * 32, v);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const bool on = (kmask[c] >> i) & 1u;
+        const float x = gated ? gate[c * 32 + i] : v[i] * a.scale;
+        const float p = (on && mx > -INFINITY) ? __expf(x - mx) : 0.f;
+        sum += p;
+        v[i] = p;
+      }
+      // unnormalised probabilities -> bf16 A operand; 1/sum is applied to the fp32 output row
+#pragma unroll
+      for (int qd = 0; qd < 4; ++qd) {
+        uint32_t w[4];
+#pragma unroll
+        for (int hh = 0; hh < 4; ++hh) w[hh] = pack_bf16(v[qd * 8 + hh * 2], v[qd * 8 + hh * 2 + 1]);
+        *reinterpret_cast<uint4 *>(sP + tile_off(128, tid, c * 32 + qd * 8)) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+    fence_proxy_async_smem();
+    fence_before_sync();
+    __syncthreads();
+
+    // ---- O = P V -----------------------------------------------------------------------------------------------------
+    if (tid == 0) {
+      fence_after_sync();
+      const uint32_t idesc = make_idesc_bf16(128, DH);
+      const uint32_t aP = smem_u32(sP), aV = smem_u32(sVt);
+#pragma unroll
+      for (int ks = 0; ks < NKP / 16; ++ks)
+        mma_bf16(tmem + COL_O, make_desc(aP + ks * 4096, 2048, 128), make_desc(aV + ks * 2 * (DH * 16), DH * 16, 128),
+                 idesc, ks > 0);
+      mma_commit(mbar);
+    }
+    mbar_wait(mbar, phase);
+    phase ^= 1u;
+    fence_after_sync();
+    {
+      const float inv = sum > 0.f ? 1.0f / sum : 0.f;
+      __nv_bfloat16 *o = a.out + (size_t)b * a.o_bs + (size_t)qi * a.o_rs + h * DH;
+#pragma unroll
+      for (int c0 = 0; c0 < DH; c0 += 32) {
+        float v[32];
+        tmem_ld32(trow + COL_O + c0, v);
+        if (qlive) {
+#pragma unroll
+          for (int qd = 0; qd < 4; ++qd) {
+            uint32_t w[4];
+#pragma unroll
+            for (int hh = 0; hh < 4; ++hh) w[hh] = pack_bf16(v[qd * 8 + hh * 2] * inv, v[qd * 8 + hh * 2 + 1] * inv);
+            *reinterpret_cast<uint4 *>(o + c0 + qd * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        }
+      }
+    }
+    fence_before_sync();  // the next tile's MMA overwrites S / O
   }
   fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc<256>(tmem);
+}
+
+template <int NCH>
+int launch_attn(const AttnArgs &a, cudaStream_t st) {
+  constexpr int NKP = NCH * 32;
+  constexpr size_t smem = (size_t)128 * DH * 2 + (size_t)NKP * DH * 2 * 2 + (size_t)128 * NKP * 2 + 32;
+  auto kern = attention_fwd_kernel<NCH>;
+  static bool configured[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !configured[dev]) {
+    int rc = sv::cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (rc) return rc;
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    configured[dev] = true;
+  }
+  kern<<<a.B * a.H, 128, smem, st>>>(a);
+  return sv::after_launch();
 }
 
 }  // namespace
@@ -236,11 +284,13 @@ extern "C" int sv_attention_fwd_bf16(const void *q, long long q_bs, int q_rs, co
   a.out = (__nv_bfloat16 *)out; a.o_bs = o_bs; a.o_rs = o_rs;
   a.kpm = key_padding_mask; a.sw = spatial_w; a.locs = pairwise_locs;
   a.B = B; a.H = H; a.SH = spatial_heads; a.Lq = Lq; a.Lk = Lk; a.NKP = (Lk + 31) / 32 * 32; a.scale = scale;
-  const size_t smem = (size_t)128 * DH * 2 + (size_t)a.NKP * DH * 2 * 2 + (size_t)128 * a.NKP * 2 + 32;
-  int rc = sv::cuda_status(
-      cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (rc) return rc;
-  dim3 grid(B * H, (Lq + 127) / 128);
-  attention_fwd_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(a);
-  return sv::after_launch();
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (a.NKP / 32) {
+    case 1: return launch_attn<1>(a, st);
+    case 2: return launch_attn<2>(a, st);
+    case 3: return launch_attn<3>(a, st);
+    case 4: return launch_attn<4>(a, st);
+    case 5: return launch_attn<5>(a, st);
+    default: return SV_ERR_INVALID_ARG;
+  }
 }
