@@ -15,8 +15,9 @@
 // a per-thread running max (thread == centre == TMEM lane) with no cross-lane traffic, and the
 // BN scale is folded into the bf16 weights so that relu(acc + shift) is monotone in acc and the
 // max can be taken on raw accumulators (affine + ReLU once per centre at the end).
-// CTA = 256 threads = two warpgroups; both cover the 128 TMEM lanes and split the COLUMNS of every
-// epilogue.  Thread 0 issues the MMAs; completion comes back through an mbarrier.
+// CTA = NCG warpgroups of 128 threads (SA1: 2, two CTAs per SM; SA2: 4, one CTA per SM): every warpgroup covers the 128 TMEM lanes (rows) and owns 1/NCG of the
+// COLUMNS of every epilogue, so 16 warps per CTA hide the TMEM-load / shared-memory latencies of the short epilogue
+// phases.  Thread 0 issues the MMAs; completion comes back through an mbarrier.
 #include <cuda_bf16.h>
 
 #include "svcommon.h"
@@ -27,8 +28,10 @@ namespace {
 
 using namespace tc05;
 
-template <int KF_, int K1P_, int N1_, int N2_, int N3_, int CPC_>
+template <int KF_, int K1P_, int N1_, int N2_, int N3_, int CPC_, int NCG_>
 struct SaCfg {
+  static constexpr int NCG = NCG_;  // column groups (warpgroups of 128 threads) per CTA
+  static constexpr int NTHREADS = 128 * NCG_;
   static constexpr int KF = KF_;    // feature channels gathered per neighbour (3 = rgb, 128 = SA1 output)
   static constexpr int K1P = K1P_;  // layer-1 K (3 + KF) padded to a multiple of 16
   static constexpr int N1 = N1_, N2 = N2_, N3 = N3_;
@@ -52,13 +55,30 @@ struct SaMlpArgs {
   int B, P, NS;
 };
 
-// relu(acc + shift) for 32 accumulator columns -> 32 bf16 written as 4 x 16 B into the A tile (row r, cols c0..c0+31)
+
+// 32 lanes x 16 columns TMEM load
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// relu(acc + shift) for NC (16 or 32) accumulator columns -> bf16, 16-byte chunks into the A tile (row r, cols c0..)
+template <int NC>
 __device__ __forceinline__ void epilogue_to_smem(uint32_t taddr, const float *__restrict__ shift, uint8_t *sA, int r,
                                                  int c0) {
-  float v[32];
-  tmem_ld32(taddr, v);
+  float v[NC];
+  if constexpr (NC == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
+  for (int q = 0; q < NC / 8; ++q) {
     uint32_t w[4];
 #pragma unroll
     for (int h = 0; h < 4; ++h) {
@@ -80,7 +100,8 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // A buffer, TMEM column range and mbarrier, so the tensor pipe works on one while the CUDA cores run the
 // epilogue / gather of the other.
 template <class Cfg, int LEVEL>
-__global__ void __launch_bounds__(256, LEVEL == 1 ? 2 : 1) sa_mlp_kernel(const SaMlpArgs a) {
+__global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::NCG == 2 ? 2 : 1) sa_mlp_kernel(const SaMlpArgs a) {
+  constexpr int NCG = Cfg::NCG, NTHREADS = Cfg::NTHREADS;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t *sW1 = smem + 2 * Cfg::A_BYTES;
   uint8_t *sW2 = sW1 + Cfg::W1_BYTES;
@@ -92,7 +113,7 @@ __global__ void __launch_bounds__(256, LEVEL == 1 ? 2 : 1) sa_mlp_kernel(const S
   uint64_t *mbar = wbar + 1;  // [2]
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(mbar + 2);
 
-  const int tid = threadIdx.x, warp = tid >> 5, wg = tid >> 7;
+  const int tid = threadIdx.x, warp = tid >> 5, wg = tid >> 7;  // wg = column group of this thread
   const int r = tid & 127;  // row of the tile == TMEM lane == centre within the super-tile
 
   if (tid == 0) {
@@ -105,7 +126,7 @@ __global__ void __launch_bounds__(256, LEVEL == 1 ? 2 : 1) sa_mlp_kernel(const S
   }
   if (warp == 1) tmem_alloc<2 * Cfg::TMEM_COLS>(tmem_slot);
   // zero both A tiles once: K-padding columns that no gather / epilogue writes stay zero for the whole kernel
-  for (int e = tid; e < 2 * Cfg::A_BYTES / 16; e += 256) reinterpret_cast<uint4 *>(smem)[e] = make_uint4(0, 0, 0, 0);
+  for (int e = tid; e < 2 * Cfg::A_BYTES / 16; e += NTHREADS) reinterpret_cast<uint4 *>(smem)[e] = make_uint4(0, 0, 0, 0);
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -167,9 +188,9 @@ __global__ void __launch_bounds__(256, LEVEL == 1 ? 2 : 1) sa_mlp_kernel(const S
       cx = c[0]; cy = c[1]; cz = c[2];
     }
     const int *my_idx = a.ball_idx + (size_t)cg * NS;
-    float runmax[Cfg::N3 / 2];
+    float runmax[Cfg::N3 / NCG];
 #pragma unroll
-    for (int i = 0; i < Cfg::N3 / 2; ++i) runmax[i] = -INFINITY;
+    for (int i = 0; i < Cfg::N3 / NCG; ++i) runmax[i] = -INFINITY;
 
     // ---- gather of row r = (centre cg, sample s) into A buffer b, split in "load" (early) and "store" -----
     struct Pre { int k; float v0, v1, v2, v3, v4, v5; };
@@ -181,7 +202,7 @@ __global__ void __launch_bounds__(256, LEVEL == 1 ? 2 : 1) sa_mlp_kernel(const S
           const float2 *q = reinterpret_cast<const float2 *>(a.pts + ((size_t)cloud * a.P + p.k) * 6);
           const float2 p0 = __ldg(q), p1 = __ldg(q + 1), p2 = __ldg(q + 2);  // x y | z r | g b
           p.v0 = p0.x; p.v1 = p0.y; p.v2 = p1.x; p.v3 = p1.y; p.v4 = p2.x; p.v5 = p2.y;
-        } else if (wg == 1) {
+        } else if (wg == NCG - 1) {
           const float *q = a.pts + ((size_t)cloud * a.P + p.k) * 3;
           p.v0 = __ldg(q); p.v1 = __ldg(q + 1); p.v2 = __ldg(q + 2);
         }
@@ -207,11 +228,11 @@ __global__ void __launch_bounds__(256, LEVEL == 1 ? 2 : 1) sa_mlp_kernel(const S
         constexpr int CH = Cfg::KF / 8;  // 16-byte chunks of the feature row
         const uint4 *f = reinterpret_cast<const uint4 *>(a.feat) + ((size_t)cloud * a.P + p.k) * CH;
 #pragma unroll
-        for (int q = 0; q < CH / 2; ++q) {
-          const int qq = wg * (CH / 2) + q;
+        for (int q = 0; q < CH / NCG; ++q) {
+          const int qq = wg * (CH / NCG) + q;
           cp_async16(sA + tile_off(128, r, qq * 8), f + qq, live ? 16u : 0u);
         }
-        if (wg == 1) {
+        if (wg == NCG - 1) {
           uint4 row = make_uint4(0, 0, 0, 0);
           if (live) {
             row.x = pack_bf16(p.v0 - cx, p.v1 - cy);
@@ -229,23 +250,19 @@ __global__ void __launch_bounds__(256, LEVEL == 1 ? 2 : 1) sa_mlp_kernel(const S
       uint8_t *sA = smem + b * Cfg::A_BYTES;
       const uint32_t tb = tmem + b * Cfg::TMEM_COLS + lane_off;
       if (L == 1) {
-#pragma unroll
-        for (int c = 0; c < Cfg::N1 / 64; ++c) {
-          const int c0 = wg * (Cfg::N1 / 2) + c * 32;
-          epilogue_to_smem(tb + c0, sh1, sA, r, c0);
-        }
+        constexpr int NC = Cfg::N1 / NCG;  // 16 or 32 columns per thread
+        const int c0 = wg * NC;
+        epilogue_to_smem<NC>(tb + c0, sh1, sA, r, c0);
       } else {
-#pragma unroll
-        for (int c = 0; c < Cfg::N2 / 64; ++c) {
-          const int c0 = wg * (Cfg::N2 / 2) + c * 32;
-          epilogue_to_smem(tb + Cfg::N1 + c0, sh2, sA, r, c0);
-        }
+        constexpr int NC = Cfg::N2 / NCG;
+        const int c0 = wg * NC;
+        epilogue_to_smem<NC>(tb + Cfg::N1 + c0, sh2, sA, r, c0);
       }
     };
     auto epi3 = [&](int b) {
-      const uint32_t tb = tmem + b * Cfg::TMEM_COLS + lane_off + wg * (Cfg::N3 / 2);
+      const uint32_t tb = tmem + b * Cfg::TMEM_COLS + lane_off + wg * (Cfg::N3 / NCG);
 #pragma unroll
-      for (int cc = 0; cc < Cfg::N3 / 64; ++cc) {
+      for (int cc = 0; cc < Cfg::N3 / (32 * NCG); ++cc) {
         float v[32];
         tmem_ld32(tb + cc * 32, v);
 #pragma unroll
@@ -302,14 +319,14 @@ __global__ void __launch_bounds__(256, LEVEL == 1 ? 2 : 1) sa_mlp_kernel(const S
     // ---- finalize: relu(max + shift3) -> bf16 row of this centre -------------------------------------------
     if (live) {
       uint4 *o = reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(a.out) + (size_t)cg * Cfg::N3 +
-                                            wg * (Cfg::N3 / 2));
+                                            wg * (Cfg::N3 / NCG));
 #pragma unroll
-      for (int q = 0; q < Cfg::N3 / 16; ++q) {
+      for (int q = 0; q < Cfg::N3 / (8 * NCG); ++q) {
         uint32_t w[4];
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
           const int c = q * 8 + h * 2;
-          const int gc = wg * (Cfg::N3 / 2) + c;
+          const int gc = wg * (Cfg::N3 / NCG) + c;
           w[h] = pack_bf16(fmaxf(runmax[c] + sh3[gc], 0.f), fmaxf(runmax[c + 1] + sh3[gc + 1], 0.f));
         }
         o[q] = make_uint4(w[0], w[1], w[2], w[3]);
@@ -324,8 +341,8 @@ __global__ void __launch_bounds__(256, LEVEL == 1 ? 2 : 1) sa_mlp_kernel(const S
   if (warp == 1) tmem_dealloc<2 * Cfg::TMEM_COLS>(tmem);
 }
 
-using Sa1 = SaCfg<3, 16, 64, 64, 128, 32>;
-using Sa2 = SaCfg<128, 144, 128, 128, 256, 16>;
+using Sa1 = SaCfg<3, 16, 64, 64, 128, 32, 2>;   // 256 threads, 2 CTAs / SM
+using Sa2 = SaCfg<128, 144, 128, 128, 256, 16, 4>;  // 512 threads, 1 CTA / SM
 
 template <class Cfg, int LEVEL>
 int launch_sa(const SaMlpArgs &a, cudaStream_t st) {
@@ -335,14 +352,15 @@ int launch_sa(const SaMlpArgs &a, cudaStream_t st) {
   int dev = 0, sms = 148, per_sm = 1;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  rc = sv::cuda_status(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, Cfg::SMEM_BYTES));
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  rc = sv::cuda_status(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, Cfg::NTHREADS, Cfg::SMEM_BYTES));
   if (rc) return rc;
   if (per_sm < 1) per_sm = 1;
   if (per_sm * 2 * Cfg::TMEM_COLS > 512) per_sm = 512 / (2 * Cfg::TMEM_COLS);  // TMEM columns are not part of the occupancy query
   const int n_super = (a.B * Cfg::CPC + 127) / 128;
   int grid = sms * per_sm;
   if (grid > n_super) grid = n_super;
-  kern<<<grid, 256, Cfg::SMEM_BYTES, st>>>(a);
+  kern<<<grid, Cfg::NTHREADS, Cfg::SMEM_BYTES, st>>>(a);
   return sv::after_launch();
 }
 
