@@ -69,6 +69,15 @@ int sv_pairwise_locs_f32(const float *centers, int row_stride, int B, int O, flo
 int sv_cross_entropy_fwd_bwd(const void *logits, long long row_stride, int is_bf16, const long long *labels, int R, int V,
                              long long ignore_index, float *loss_rows, void *grad_logits, void *stream);
 
+/* L2-normalise + all-gather fused over NVLink peer memory (reference: contra_loss.py:58-64,86-91 + dist_utils.py:131-149).
+ * a, b: local (n,D) f32.  peer_bufs[world] / peer_signals[world]: DEVICE arrays of device pointers into a symmetric
+ * allocation mapped on every rank: buffer = [2 parities][2 tensors][world*n][D] f32, signal = >= world uint32 words
+ * (zero-initialised).  epoch must start at 1 and increase by 1 per call on every rank.  When the kernel completes the
+ * local buffer holds, for parity epoch&1, normalize(a) and normalize(b) of all ranks in rank-major order. */
+int sv_normalize_allgather_f32(const float *a, const float *b, int n, int D, void *const *peer_bufs,
+                               void *const *peer_signals, unsigned *done_counter, int world, int rank, unsigned epoch,
+                               void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -57,6 +57,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
   uint64_t *acc_full = empty + STAGES;   // [2]
   uint64_t *acc_empty = acc_full + 2;    // [2]
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+  float *stage = reinterpret_cast<float *>(tmem_slot + 4);  // [4 warps][32][33] transpose scratch (row-max epilogue)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_m = (g.M + BM - 1) / BM, tiles_n = (g.N + BN - 1) / BN;
@@ -146,22 +147,30 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
             v[i] = x;
           }
           if (g.rowmax == 16) {
-            // max over the 16 rows of each half-warp (rows are consecutive points of one cloud)
+            // max over the 16 rows of each half-warp (16 consecutive rows = the 16 points of one cloud): the warp
+            // transposes its 32x32 chunk through shared memory so that lane i reduces column i of both groups
+            float *tp = stage + (warp - 2) * (32 * 33);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              float x = row < g.M ? v[i] : -INFINITY;
+            for (int i = 0; i < 32; ++i) tp[lane * 33 + i] = row < g.M ? v[i] : -INFINITY;
+            __syncwarp();
+            float ga = -INFINITY, gb = -INFINITY;
 #pragma unroll
-              for (int o = 8; o > 0; o >>= 1) x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, o));
-              v[i] = x;
+            for (int rr = 0; rr < 16; ++rr) {
+              ga = fmaxf(ga, tp[rr * 33 + lane]);
+              gb = fmaxf(gb, tp[(rr + 16) * 33 + lane]);
             }
-            if ((lane & 15) == 0 && row < g.M) {
-              const size_t orow = (size_t)(row >> 4);
-              if (g.out_f32) {
-                float *o = reinterpret_cast<float *>(g.out) + orow * g.ldo + col0;
-                for (int i = 0; i < 32 && col0 + i < g.N; ++i) o[i] = v[i];
-              } else {
-                __nv_bfloat16 *o = reinterpret_cast<__nv_bfloat16 *>(g.out) + orow * g.ldo + col0;
-                for (int i = 0; i < 32 && col0 + i < g.N; ++i) o[i] = __float2bfloat16_rn(v[i]);
+            __syncwarp();
+            const int wrow0 = m0 + q * 32;  // first accumulator row of this warp
+            const int col = col0 + lane;
+            if (col < g.N) {
+              const size_t orow = (size_t)(wrow0 >> 4);
+              if (wrow0 < g.M) {
+                if (g.out_f32) reinterpret_cast<float *>(g.out)[orow * g.ldo + col] = ga;
+                else reinterpret_cast<__nv_bfloat16 *>(g.out)[orow * g.ldo + col] = __float2bfloat16_rn(ga);
+              }
+              if (wrow0 + 16 < g.M) {
+                if (g.out_f32) reinterpret_cast<float *>(g.out)[(orow + 1) * g.ldo + col] = gb;
+                else reinterpret_cast<__nv_bfloat16 *>(g.out)[(orow + 1) * g.ldo + col] = __float2bfloat16_rn(gb);
               }
             }
           } else if (row < g.M) {
@@ -244,7 +253,7 @@ int make_map(CUtensorMap *map, const void *ptr, int rows, int K, int ld, int box
 
 template <int BN>
 int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mb, const GemmArgs &g, cudaStream_t st) {
-  constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + (2 * STAGES + 4) * 8 + 16;
+  constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + (2 * STAGES + 4) * 8 + 16 + 4 * 32 * 33 * 4;
   auto kern = gemm_kernel<BN>;
   static int sms_of_dev[64] = {0};  // also marks "attribute set on this device" (one-time host work per device)
   int dev = 0;

@@ -72,10 +72,19 @@ class _SymmetricInfoNCE(nn.Module):
 
     def info_nce(self, a_feats, text_feats):
         logit_scale = torch.clamp(self.logit_scale, max=100)
-        a_feats = F.normalize(a_feats, dim=-1, p=2)
-        text_feats = F.normalize(text_feats, dim=-1, p=2)
-        if self.distributed:
-            a_feats, text_feats = all_gather([a_feats, text_feats])
+        fused = None
+        if self.distributed and a_feats.is_cuda and dist.is_initialized() and dist.get_backend() == "nccl":
+            from .. import fused_gather
+            fused = fused_gather.get(a_feats.shape[0], a_feats.shape[1], a_feats.device)
+        if fused is not None:
+            # one kernel: normalise both sets and store them into every rank's buffer over NVLink (detached, like the
+            # reference's gather)
+            a_feats, text_feats = fused(a_feats, text_feats)
+        else:
+            a_feats = F.normalize(a_feats, dim=-1, p=2)
+            text_feats = F.normalize(text_feats, dim=-1, p=2)
+            if self.distributed:
+                a_feats, text_feats = all_gather([a_feats, text_feats])
         labels = torch.arange(text_feats.shape[0], device=text_feats.device)
         t2a = logit_scale * text_feats @ a_feats.t()
         a2t = logit_scale * a_feats @ text_feats.t()
