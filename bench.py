@@ -308,8 +308,13 @@ def main():
            "data": "synthetic", "config": config, "final_loss": loss,
            "e2e": {"value": e2e_value, "unit": "scenes/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
            "gpu_launches": int(launches), "clocks": clocks,
-           "native_kernels_in_step": ["sa_sample_kernel (FPS+ball query x2 levels)", "sa_mlp_kernel<SA1>", "sa_mlp_kernel<SA2>"],
-           "library_ops_in_step": [k for k, v in ops.NATIVE.items() if not v] + ["SA3+fc", "BERT-4L (HF)", "AdamW (torch fused)", "NCCL"]}
+           "native_kernels_in_step": ["sa_sample_kernel (FPS + ball query, 2 SA levels)", "sa_mlp_kernel<SA1>", "sa_mlp_kernel<SA2>",
+                                      "gemm_kernel x4 (SA3 chain + fc, fused shift/ReLU/row-max)", "pairwise_locs_kernel",
+                                      "attention_fwd_kernel (spatial gate) x4", "ce_fwd_bwd_kernel (masked-LM CE)",
+                                      "norm_allgather_kernel (N > 1: contrastive exchange over NVLink peer memory)"],
+           "library_ops_in_step": ["plain linears (cuBLAS)", "nn.MultiheadAttention core with dropout (cuDNN SDPA)", "LayerNorm / dropout / residual (ATen)",
+                                   "spatial-attention backward (torch recompute)", "BERT-4L (HF, upstream of the path)", "AdamW (torch fused)",
+                                   "gradient all-reduce (NCCL via DDP)"]}
     if rt is not None:
         out["roofline"], out["roofline_pointops"] = rt, rp
     if not args.no_cpu_baseline:
