@@ -3,7 +3,7 @@ import torch
 from torch import nn
 
 from .. import ops
-from .layers import get_activation_fn, get_mlp_head
+from .layers import get_mlp_head
 from .registry import HEADS_REGISTRY
 
 
@@ -39,34 +39,41 @@ class GroundHead(nn.Module):
         return og3d_logits
 
 
-class BertPredictionHeadTransform(nn.Module):
-    def __init__(self, hidden_size, hidden_act='gelu'):
-        super().__init__()
-        self.dense = nn.Linear(hidden_size, hidden_size)
-        self.act_name = hidden_act
-        self.transform_act_fn = get_activation_fn(hidden_act)
-        self.LayerNorm = nn.LayerNorm(hidden_size)
+class _Transform(nn.Module):
+    """dense -> gelu -> LayerNorm; parameter names `dense.*`, `LayerNorm.*` as in pretrain_head.py:8-19."""
 
-    def forward(self, hidden_states):
-        return self.LayerNorm(ops.linear(hidden_states, self.dense.weight, self.dense.bias, activation=self.act_name))
+    def __init__(self, width):
+        super().__init__()
+        self.dense, self.LayerNorm = nn.Linear(width, width), nn.LayerNorm(width)
 
 
 class BertLMPredictionHead(nn.Module):
+    """BERT masked-LM head (pretrain_head.py:22-32): logits = decoder(LayerNorm(gelu(dense(h)))) + bias, with the
+    state_dict keys `transform.dense.*`, `transform.LayerNorm.*`, `decoder.weight`, `bias`.  The dense+gelu and the
+    decoder+bias steps go through `ops.linear` so that they pick up fused epilogues."""
+
     def __init__(self, hidden_size, vocab_size):
         super().__init__()
-        self.transform = BertPredictionHeadTransform(hidden_size=hidden_size, hidden_act='gelu')
+        self.transform = _Transform(hidden_size)
         self.decoder = nn.Linear(hidden_size, vocab_size, bias=False)
         self.bias = nn.Parameter(torch.zeros(vocab_size))
 
     def forward(self, hidden_states):
-        return ops.linear(self.transform(hidden_states), self.decoder.weight, self.bias)
+        t = self.transform
+        h = t.LayerNorm(ops.linear(hidden_states, t.dense.weight, t.dense.bias, activation="gelu"))
+        return ops.linear(h, self.decoder.weight, self.bias)
+
+
+def _lm_heads(owner, hidden_size, **vocabs):
+    for name, size in vocabs.items():
+        setattr(owner, name, BertLMPredictionHead(hidden_size, size))
 
 
 @HEADS_REGISTRY.register()
 class PretrainHeadV1(nn.Module):
     def __init__(self, cfg, hidden_size=768, vocab_size=30522):
         super().__init__()
-        self.lm_pred_head = BertLMPredictionHead(hidden_size, vocab_size)
+        _lm_heads(self, hidden_size, lm_pred_head=vocab_size)
 
     def forward(self, txt_embeds, **kwargs):
         return self.lm_pred_head(txt_embeds)
@@ -76,8 +83,7 @@ class PretrainHeadV1(nn.Module):
 class OVPretrainHead(nn.Module):
     def __init__(self, cfg, hidden_size=768, vocab_size=30522, obj_vocab_size=607):
         super().__init__()
-        self.lm_pred_head = BertLMPredictionHead(hidden_size, vocab_size)
-        self.obj_pred_head = BertLMPredictionHead(hidden_size, obj_vocab_size)
+        _lm_heads(self, hidden_size, lm_pred_head=vocab_size, obj_pred_head=obj_vocab_size)
 
     def forward(self, txt_embeds, obj_embeds, **kwargs):
         return self.lm_pred_head(txt_embeds), self.obj_pred_head(obj_embeds)
