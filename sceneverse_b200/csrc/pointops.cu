@@ -661,6 +661,11 @@ int sv_fps_f32(const float *xyz, int B, int N, int m, int *idx, float *new_xyz, 
     if (g.spt <= 16) return launch_fps_block<16>(xyz, B, N, m, g, idx, new_xyz, st);
     if (g.spt <= 32) return launch_fps_block<32>(xyz, B, N, m, g, idx, new_xyz, st);
   }
+  {
+    // large clouds: register-resident slices on co-resident CTAs (csrc/fps_coop.cu); shapes that do not fit fall through
+    const int rc_coop = sv::fps_coop(xyz, B, N, m, idx, new_xyz, st);
+    if (rc_coop != SV_ERR_INVALID_ARG) return rc_coop;
+  }
   const FpsGeom g = fps_geom(N, 5);
   float *temp = nullptr;
   int rc = get_scratch((size_t)B * N * sizeof(float), st, &temp);

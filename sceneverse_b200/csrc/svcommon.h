@@ -35,4 +35,7 @@ inline int cuda_status(cudaError_t e) {
 // the FPS tie-break order, so it is reproduced with the same libm expression.
 int ref_opt_n_threads(int work_size);
 
+// csrc/fps_coop.cu: multi-CTA register-resident FPS for 8192 < N; SV_ERR_INVALID_ARG = shape not supported by this path
+int fps_coop(const float *xyz, int B, int N, int m, int *idx, float *new_xyz, cudaStream_t st);
+
 }  // namespace sv

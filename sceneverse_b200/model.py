@@ -144,6 +144,21 @@ def pretrain_config(num_gpu=1, with_obj_between=True, text_features=None):
     }
 
 
+def scanrefer_config(num_gpu=1, text_features=None):
+    """configs/final/finetune/scanrefer_finetune.yaml:205-259 — BASELINE.json configs[2]: same encoders, GroundHeadV1
+    (hidden 384, detach_all_aux_loss) and `og3d_loss`; the backbone stays frozen, no scene captions."""
+    cfg = pretrain_config(num_gpu, text_features=text_features)
+    cfg["data"]["args"]["use_scene_cap"] = False
+    cfg["solver"]["lr"] = 1e-4
+    cfg["model"]["heads"] = {"head_list": ["ground_head"],
+                             "ground_head": {"name": "GroundHeadV1",
+                                             "args": {"hidden_size": 384, "input_size": 768, "sem_cls_size": 607,
+                                                      "dropout": 0.3, "detach_all_aux_loss": True}}}
+    cfg["model"]["loss_list"] = ["og3d_loss"]
+    cfg["model"]["vis_loss_list"] = ["og3d_loss"]
+    return cfg
+
+
 def warmup_cosine(step, warmup_step, total_step, minimum_ratio=1e-5):
     """optim/scheduler.py warmup_cosine (LambdaLR factor)."""
     import math

@@ -28,6 +28,10 @@ def fps_cases_large():
     cases["adversarial_n2048"] = (np.stack([adv[k] for k in sorted(adv)]), 24)
     adv = synthetic.adversarial_clouds(10, 9000)
     cases["adversarial_n9000"] = (np.stack([adv[k] for k in sorted(adv)]), 12)
+    cases["ball_n65536"] = (synthetic.unit_ball_clouds(77, 3, 65536), 40)          # 16 CTAs per cloud
+    cases["ball_n300000_b2"] = (synthetic.unit_ball_clouds(78, 2, 300000), 6)      # 74 CTAs per cloud, 2 waves of clouds
+    adv = synthetic.adversarial_clouds(11, 16384)
+    cases["adversarial_n16384"] = (np.stack([adv[k] for k in sorted(adv)]), 16)
     return cases
 
 
