@@ -206,7 +206,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="gps_pretrain", choices=["gps_pretrain", "pointops_sa1"])
+    ap.add_argument("--workload", default="gps_pretrain", choices=["gps_pretrain", "pointops_sa1", "pointops_sweep"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-rooflines", action="store_true")
     args = ap.parse_args()
@@ -236,6 +236,50 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     stream = torch.cuda.current_stream()
+
+    if args.workload == "pointops_sweep":
+        # BASELINE.json configs[4]: FPS (m = N/32) + ball query (M = m centres, r = 0.2*(1024/N)^(1/3), nsample 32) on
+        # unit-ball clouds, batch sharded over the ranks; Mpts/s = B*N / t, roofline = 28.5 algorithmic bytes per point
+        from sceneverse_b200 import synthetic
+        hbm, _, src = peaks()
+        rows = []
+        for (Bt, N) in [(256, 16384), (64, 16384), (16, 65536), (4, 262144), (1, 1048576)]:
+            Bl = max(1, Bt // world)
+            x = torch.from_numpy(synthetic.unit_ball_clouds(7 + rank, min(Bl, 8), N)).to(device)
+            x = x.repeat((Bl + x.shape[0] - 1) // x.shape[0], 1, 1)[:Bl].contiguous()
+            m, r = N // 32, 0.2 * (1024.0 / N) ** (1.0 / 3.0)
+            idx = _ext.furthest_point_sampling(x, m)
+            cen = torch.gather(x, 1, idx.long()[..., None].expand(-1, -1, 3)).contiguous()
+            _ext.ball_query(cen, x, r, 32)
+            torch.cuda.synchronize()
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            e[0].record(stream)
+            idx = _ext.furthest_point_sampling(x, m)
+            e[1].record(stream)
+            _ext.ball_query(cen, x, r, 32)
+            e[2].record(stream)
+            torch.cuda.synchronize()
+            t = torch.tensor([e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2])], device=device, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            tf_, tb_ = float(t[0]), float(t[1])
+            pts = Bl * world * N
+            ach = pts * 28.5 / ((tf_ + tb_) * 1e-3) / 1e9
+            rows.append({"batch": Bl * world, "N": N, "m": m, "radius": r, "fps_ms": tf_, "ball_query_ms": tb_,
+                         "mpts_per_s": pts / ((tf_ + tb_) * 1e-3) / 1e6, "hbm_frac": ach / hbm})
+        if world > 1:
+            dist.destroy_process_group()
+        if rank == 0:
+            best = max(rows, key=lambda r_: r_["mpts_per_s"])
+            print(json.dumps({"metric": "FPS+ball_query Mpts/s (sweep 16K-1M points)", "value": best["mpts_per_s"], "unit": "Mpts/s",
+                              "n_gpus": world, "steps": 1, "warmup": 1, "ms_per_step": best["fps_ms"] + best["ball_query_ms"],
+                              "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                              "data": "synthetic", "config": {"workload": "pointops_sweep", "parallelism": f"dp{world}"},
+                              "sweep": rows, "roofline": {"bound": "hbm", "peak": hbm, "unit": "GB/s", "peak_source": src,
+                                                          "achieved": best["hbm_frac"] * hbm, "frac": best["hbm_frac"], "traffic": None,
+                                                          "note": "FPS is bound by the m-1 serial arg-max steps (one L2 exchange per step for N > 8192), not by HBM"},
+                              "gpu_launches": 2 * len(rows)}))
+        return 0
 
     if args.workload == "pointops_sa1":
         rt, rp = kernel_rooflines(torch, device)

@@ -36,8 +36,12 @@ struct SaCfg {
   static constexpr int K1P = K1P_;  // layer-1 K (3 + KF) padded to a multiple of 16
   static constexpr int N1 = N1_, N2 = N2_, N3 = N3_;
   static constexpr int CPC = CPC_;  // centres per cloud (npoint of this level)
-  static constexpr int KMAX = K1P > N1 ? (K1P > N2 ? K1P : N2) : (N1 > N2 ? N1 : N2);
-  static constexpr int A_BYTES = 128 * KMAX * 2;
+  // Operand layout: columns [0, KSW) of a layer's K live in SWIZZLE_128B slabs of 64 columns, the remaining (< 64)
+  // columns — only the layer-1 tail (SA1: all 16, SA2: xyz, columns 128..143) — in a no-swizzle tail block behind them.
+  static constexpr int KSW1 = (K1P / 64) * 64, KT1 = K1P - KSW1;  // layer 1: swizzled / tail columns
+  static constexpr int SWMAX = (N1 > N2 ? N1 : N2) > KSW1 ? (N1 > N2 ? N1 : N2) : KSW1;
+  static constexpr int A_TAIL_OFF = (SWMAX / 64) * (128 * 128);   // tail block of the A tile
+  static constexpr int A_BYTES = A_TAIL_OFF + 128 * 16 * 2;        // + 16 tail columns
   static constexpr int W1_BYTES = N1 * K1P * 2, W2_BYTES = N2 * N1 * 2, W3_BYTES = N3 * N2 * 2;
   static constexpr int SHIFT_BYTES = (N1 + N2 + N3) * 4;
   static constexpr int PARAM_BYTES = W1_BYTES + W2_BYTES + W3_BYTES + SHIFT_BYTES;
@@ -86,7 +90,7 @@ __device__ __forceinline__ void epilogue_to_smem(uint32_t taddr, const float *__
       const float a = fmaxf(v[c] + shift[c0 + c], 0.f), b = fmaxf(v[c + 1] + shift[c0 + c + 1], 0.f);
       w[h] = pack_bf16(a, b);
     }
-    *reinterpret_cast<uint4 *>(sA + tile_off(128, r, c0 + q * 8)) = make_uint4(w[0], w[1], w[2], w[3]);
+    *reinterpret_cast<uint4 *>(sA + tile_off_sw128(128, r, c0 + q * 8)) = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
 
@@ -144,21 +148,27 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::NCG == 2 ? 2 : 1) sa_mlp_k
     fence_after_sync();
     const uint32_t aA = smem_u32(smem + b * Cfg::A_BYTES);
     const uint32_t tb = tmem + b * Cfg::TMEM_COLS;
+    // K-step ks of a layer with K columns: swizzled slab addressing for columns < KSW, no-swizzle tail behind
+    auto step = [&](uint32_t acc, uint32_t aW, int N, int KSW, int ks, uint32_t idesc) {
+      const int c0 = ks * 16;
+      if (c0 < KSW) {
+        mma_bf16(acc, make_desc_sw128(aA + (c0 >> 6) * (128 * 128) + ((c0 >> 4) & 3) * 32),
+                 make_desc_sw128(aW + (c0 >> 6) * (N * 128) + ((c0 >> 4) & 3) * 32), idesc, ks > 0);
+      } else {
+        const int kt = (c0 - KSW) >> 4;
+        mma_bf16(acc, make_desc(aA + Cfg::A_TAIL_OFF + kt * 4096, 2048, 128),
+                 make_desc(aW + (KSW >> 6) * (N * 128) + kt * 2 * (N * 16), N * 16, 128), idesc, ks > 0);
+      }
+    };
     if (L == 1) {
 #pragma unroll
-      for (int ks = 0; ks < Cfg::K1P / 16; ++ks)
-        mma_bf16(tb, make_desc(aA + ks * 4096, 2048, 128), make_desc(aW1 + ks * 2 * (Cfg::N1 * 16), Cfg::N1 * 16, 128),
-                 IDESC1, ks > 0);
+      for (int ks = 0; ks < Cfg::K1P / 16; ++ks) step(tb, aW1, Cfg::N1, Cfg::KSW1, ks, IDESC1);
     } else if (L == 2) {
 #pragma unroll
-      for (int ks = 0; ks < Cfg::N1 / 16; ++ks)
-        mma_bf16(tb + Cfg::N1, make_desc(aA + ks * 4096, 2048, 128),
-                 make_desc(aW2 + ks * 2 * (Cfg::N2 * 16), Cfg::N2 * 16, 128), IDESC2, ks > 0);
+      for (int ks = 0; ks < Cfg::N1 / 16; ++ks) step(tb + Cfg::N1, aW2, Cfg::N2, Cfg::N1, ks, IDESC2);
     } else {
 #pragma unroll
-      for (int ks = 0; ks < Cfg::N2 / 16; ++ks)
-        mma_bf16(tb, make_desc(aA + ks * 4096, 2048, 128), make_desc(aW3 + ks * 2 * (Cfg::N3 * 16), Cfg::N3 * 16, 128),
-                 IDESC3, ks > 0);
+      for (int ks = 0; ks < Cfg::N2 / 16; ++ks) step(tb, aW3, Cfg::N3, Cfg::N2, ks, IDESC3);
     }
     mma_commit(mbar + b);
   };
@@ -219,9 +229,7 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::NCG == 2 ? 2 : 1) sa_mlp_k
             row.y = pack_bf16(p.v2 - cz, p.v3);
             row.z = pack_bf16(p.v4, p.v5);
           }
-          *reinterpret_cast<uint4 *>(sA + tile_off(128, r, 0)) = row;
-          // columns 8..15 are K padding that the layer-1/2 epilogues overwrite: re-zero every tile
-          *reinterpret_cast<uint4 *>(sA + tile_off(128, r, 8)) = make_uint4(0, 0, 0, 0);
+          *reinterpret_cast<uint4 *>(sA + Cfg::A_TAIL_OFF + tile_off(128, r, 0)) = row;  // columns 8..15 stay zero
         }
       } else {
         // columns [0,KF) = features of the neighbour, [KF,KF+3) = xyz - centre (weights permuted to match)
@@ -230,7 +238,7 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::NCG == 2 ? 2 : 1) sa_mlp_k
 #pragma unroll
         for (int q = 0; q < CH / NCG; ++q) {
           const int qq = wg * (CH / NCG) + q;
-          cp_async16(sA + tile_off(128, r, qq * 8), f + qq, live ? 16u : 0u);
+          cp_async16(sA + tile_off_sw128(128, r, qq * 8), f + qq, live ? 16u : 0u);
         }
         if (wg == NCG - 1) {
           uint4 row = make_uint4(0, 0, 0, 0);
@@ -238,7 +246,7 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::NCG == 2 ? 2 : 1) sa_mlp_k
             row.x = pack_bf16(p.v0 - cx, p.v1 - cy);
             row.y = pack_bf16(p.v2 - cz, 0.f);
           }
-          *reinterpret_cast<uint4 *>(sA + tile_off(128, r, Cfg::KF)) = row;
+          *reinterpret_cast<uint4 *>(sA + Cfg::A_TAIL_OFF + tile_off(128, r, 0)) = row;  // tail columns 8..15 stay zero
         }
       }
     };

@@ -130,4 +130,11 @@ __device__ __forceinline__ uint32_t tile_off(uint32_t rows, uint32_t r, uint32_t
   return (k >> 3) * (rows * 16u) + r * 16u + (k & 7u) * 2u;
 }
 
+// byte offset of element (row r, column k) in a K-major SWIZZLE_128B tile: slabs of 64 columns (rows x 128 B each),
+// 8-row groups of 1024 B, the 16-byte chunk index XOR-ed with (r & 7) — the layout TMA writes with
+// CU_TENSOR_MAP_SWIZZLE_128B and make_desc_sw128 reads.  The tile base must be 1024-byte aligned.
+__device__ __forceinline__ uint32_t tile_off_sw128(uint32_t rows, uint32_t r, uint32_t k) {
+  return (k >> 6) * (rows * 128u) + (r >> 3) * 1024u + (r & 7u) * 128u + ((((k >> 3) & 7u) ^ (r & 7u)) << 4) + (k & 7u) * 2u;
+}
+
 }  // namespace tc05

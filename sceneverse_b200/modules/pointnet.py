@@ -86,6 +86,24 @@ def to_umma_kmajor(w):
     return w.to(torch.bfloat16).reshape(n, k // 8, 8).permute(1, 0, 2).contiguous()
 
 
+def to_umma_sw128(w):
+    """(N,K) -> bf16 operand image for csrc/sa_mlp.cu: the first floor(K/64)*64 columns as SWIZZLE_128B K-major slabs
+    ([slab][N][8 chunks][8], chunk position = chunk ^ (n & 7)), the remaining (< 64) columns as a no-swizzle K-major
+    tail ([K/8][N][8])."""
+    n, k = w.shape
+    ksw = (k // 64) * 64
+    wb = w.to(torch.bfloat16)
+    parts = []
+    if ksw:
+        sl = wb[:, :ksw].reshape(n, ksw // 64, 8, 8)                      # (n, slab, chunk, 8)
+        pos = torch.arange(8, device=w.device)[None, :] ^ (torch.arange(n, device=w.device)[:, None] & 7)  # chunk stored at position p
+        sl = torch.gather(sl, 2, pos[:, None, :, None].expand(n, ksw // 64, 8, 8))   # out[n,s,p] = in[n,s,p ^ (n&7)]
+        parts.append(sl.permute(1, 0, 2, 3).contiguous().reshape(-1))
+    if k > ksw:
+        parts.append(to_umma_kmajor(wb[:, ksw:].contiguous()).reshape(-1))
+    return torch.cat(parts).contiguous()
+
+
 def pack_sa_params(level, layers):
     """layers = 3 x (W' (Cout,Cin) f32, shift (Cout) f32) in the REFERENCE channel order
     (cat([grouped_xyz(3), grouped_features(C)]), pointnet2_utils.py:354-356).  Returns a uint8 CUDA tensor laid out as
@@ -101,8 +119,8 @@ def pack_sa_params(level, layers):
         w1p = torch.zeros(w1.shape[0], k1p, device=dev)
         w1p[:, :128] = w1[:, 3:]   # kernel column order: features first ...
         w1p[:, 128:131] = w1[:, :3]  # ... then xyz - centre
-    parts = [to_umma_kmajor(w1p).view(torch.uint8).reshape(-1), to_umma_kmajor(w2).view(torch.uint8).reshape(-1),
-             to_umma_kmajor(w3).view(torch.uint8).reshape(-1),
+    parts = [to_umma_sw128(w1p).view(torch.uint8).reshape(-1), to_umma_sw128(w2).view(torch.uint8).reshape(-1),
+             to_umma_sw128(w3).view(torch.uint8).reshape(-1),
              torch.cat([s1, s2, s3]).float().contiguous().view(torch.uint8).reshape(-1)]
     buf = torch.cat(parts).contiguous()
     want = _lib.gps().sv_sa_mlp_param_bytes(level)
