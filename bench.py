@@ -302,9 +302,31 @@ def main():
     def step_resident(i):
         return ps.step(dict(resident[i % NBUF]))
 
+    # e2e: every step's inputs travel host -> device inside the timed region; the copy of step i+1 is issued on a
+    # side stream while step i computes (two device-side staging slots), the loss is read back to pinned host memory
+    copy_stream = torch.cuda.Stream(device=device)
+    slots = [{k: torch.empty_like(v, device=device) for k, v in pinned[0].items()} for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    state = {"primed": -1}
+
+    def upload(i):
+        s = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[s])
+            for k, v in pinned[i % NBUF].items():
+                slots[s][k].copy_(v, non_blocking=True)
+            ready[s].record(copy_stream)
+
     def step_e2e(i):
-        batch = {k: v.to(device, non_blocking=True) for k, v in pinned[i % NBUF].items()}
-        loss = ps.step(batch)
+        if state["primed"] != i:   # first call of a timed loop: nothing was prefetched for it
+            upload(i)
+        upload(i + 1)
+        state["primed"] = i + 1
+        s = i % 2
+        stream.wait_event(ready[s])
+        loss = ps.step(dict(slots[s]))
+        consumed[s].record(stream)
         host_loss.copy_(loss.float(), non_blocking=True)
         return loss
 
