@@ -56,6 +56,23 @@ int sv_attention_fwd_bf16(const void *q, long long q_bs, int q_rs, const void *k
                           const unsigned char *key_padding_mask, const float *spatial_w, int spatial_heads,
                           const float *pairwise_locs, int B, int H, int Lq, int Lk, float scale, void *stream);
 
+/* same as sv_attention_fwd_bf16, additionally storing lse (B,H,Lq) f32 = log-sum-exp of each query's logits (needed by
+ * sv_attention_bwd_bf16) */
+int sv_attention_fwd_lse_bf16(const void *q, long long q_bs, int q_rs, const void *k, long long k_bs, int k_rs,
+                              const void *v, long long v_bs, int v_rs, void *out, long long o_bs, int o_rs,
+                              const unsigned char *key_padding_mask, const float *spatial_w, int spatial_heads,
+                              const float *pairwise_locs, int B, int H, int Lq, int Lk, float scale, float *lse,
+                              void *stream);
+/* Backward of the fused attention (two tcgen05 kernels: dQ + gate-weight gradients with thread == query, dK/dV with
+ * thread == key; both recompute P from Q, K, the gate and lse).  q/k/v as in the forward; o, d_o (B,Lq,H*64) bf16
+ * contiguous; dq (B,Lq,H*64), dk, dv (B,Lk,H*64) bf16 contiguous; d_spatial_w (B,Lq,H*6) f32 (NULL without gate; gate
+ * requires spatial_heads == H); dvec (B,H,Lq) f32 scratch.  Lq, Lk <= 160. */
+int sv_attention_bwd_bf16(const void *q, long long q_bs, int q_rs, const void *k, long long k_bs, int k_rs,
+                          const void *v, long long v_bs, int v_rs, const void *o, const void *d_o,
+                          const unsigned char *key_padding_mask, const float *spatial_w, const float *pairwise_locs,
+                          const float *lse, int B, int H, int Lq, int Lk, float scale, void *dq, void *dk, void *dv,
+                          float *d_spatial_w, float *dvec, void *stream);
+
 /* calc_pairwise_locs, 'center' relation (reference: modules/utils.py:38-87): centers (B,O,*) f32 with row stride
  * row_stride (>= 3 floats; xyz first) -> out (B,O,O,5) f32 = [dist/max_dist, dz/dist, dist2d/dist, dy/dist2d, dx/dist2d];
  * dist_norm = 0 keeps the raw distance in slot 0.  eps sits inside the square roots (1e-10 in the reference). */

@@ -71,6 +71,12 @@ _GPS_SIGS = {
                                  c_void_p, c_void_p],
     "sv_normalize_allgather_f32": [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                    ctypes.c_uint, c_void_p],
+    "sv_attention_fwd_lse_bf16": [c_void_p, ctypes.c_longlong, c_int, c_void_p, ctypes.c_longlong, c_int, c_void_p,
+                                  ctypes.c_longlong, c_int, c_void_p, ctypes.c_longlong, c_int, c_void_p, c_void_p, c_int,
+                                  c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p],
+    "sv_attention_bwd_bf16": [c_void_p, ctypes.c_longlong, c_int, c_void_p, ctypes.c_longlong, c_int, c_void_p,
+                              ctypes.c_longlong, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                              c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "sv_sa_mlp_param_bytes": [c_int],
     "sv_sa1_mlp_bf16": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
     "sv_sa2_mlp_bf16": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],

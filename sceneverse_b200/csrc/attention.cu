@@ -32,6 +32,7 @@ struct AttnArgs {
   const float *locs;               // (B,Lq,Lk,5)
   int B, H, SH, Lq, Lk, NKP;       // NKP = Lk rounded up to a multiple of 32
   float scale;
+  float *lse;                      // (B,H,Lq) log-sum-exp of the logits per query (for the backward), or null
 };
 
 constexpr int DH = 64;
@@ -221,6 +222,7 @@ __global__ void __launch_bounds__(128, 2) attention_fwd_kernel(const AttnArgs a)
     fence_after_sync();
     {
       const float inv = sum > 0.f ? 1.0f / sum : 0.f;
+      if (a.lse != nullptr && qlive) a.lse[((size_t)b * a.H + h) * a.Lq + qi] = sum > 0.f ? mx + __logf(sum) : INFINITY;
       __nv_bfloat16 *o = a.out + (size_t)b * a.o_bs + (size_t)qi * a.o_rs + h * DH;
 #pragma unroll
       for (int c0 = 0; c0 < DH; c0 += 32) {
@@ -269,6 +271,15 @@ extern "C" int sv_attention_fwd_bf16(const void *q, long long q_bs, int q_rs, co
                                      const unsigned char *key_padding_mask, const float *spatial_w, int spatial_heads,
                                      const float *pairwise_locs, int B, int H, int Lq, int Lk, float scale,
                                      void *stream) {
+  return sv_attention_fwd_lse_bf16(q, q_bs, q_rs, k, k_bs, k_rs, v, v_bs, v_rs, out, o_bs, o_rs, key_padding_mask,
+                                   spatial_w, spatial_heads, pairwise_locs, B, H, Lq, Lk, scale, nullptr, stream);
+}
+
+extern "C" int sv_attention_fwd_lse_bf16(const void *q, long long q_bs, int q_rs, const void *k, long long k_bs, int k_rs,
+                                         const void *v, long long v_bs, int v_rs, void *out, long long o_bs, int o_rs,
+                                         const unsigned char *key_padding_mask, const float *spatial_w,
+                                         int spatial_heads, const float *pairwise_locs, int B, int H, int Lq, int Lk,
+                                         float scale, float *lse, void *stream) {
   if (B < 0 || H < 1 || Lq < 0 || Lk < 1 || Lk > 160) return SV_ERR_INVALID_ARG;
   if (B == 0 || Lq == 0) return SV_OK;
   if (!q || !k || !v || !out) return SV_ERR_INVALID_ARG;
@@ -284,6 +295,7 @@ extern "C" int sv_attention_fwd_bf16(const void *q, long long q_bs, int q_rs, co
   a.out = (__nv_bfloat16 *)out; a.o_bs = o_bs; a.o_rs = o_rs;
   a.kpm = key_padding_mask; a.sw = spatial_w; a.locs = pairwise_locs;
   a.B = B; a.H = H; a.SH = spatial_heads; a.Lq = Lq; a.Lk = Lk; a.NKP = (Lk + 31) / 32 * 32; a.scale = scale;
+  a.lse = lse;
   cudaStream_t st = (cudaStream_t)stream;
   switch (a.NKP / 32) {
     case 1: return launch_attn<1>(a, st);

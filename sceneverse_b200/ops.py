@@ -10,7 +10,7 @@ import torch.nn.functional as F
 
 NATIVE = {"linear": False,              # plain GEMM -> cuBLAS (library GEMM); fused GEMMs (SA3, fc) use native.gemm
           "attention": "eval",          # nn.MultiheadAttention core: native tcgen05 kernel when no attention dropout is needed
-          "spatial_attention": True,    # MultiHeadAttentionSpatial core: native tcgen05 forward (+ recompute backward)
+          "spatial_attention": True,    # MultiHeadAttentionSpatial core: native tcgen05 forward and backward
           "calc_pairwise_locs": True,
           "cross_entropy": True}        # masked-LM / grounding CE: fused native forward+gradient
 
@@ -19,8 +19,30 @@ def _native_ok(*tensors):
     return all(t.is_cuda and t.dtype == torch.bfloat16 for t in tensors)
 
 
-class _SpatialAttentionFn(torch.autograd.Function):
-    """Native forward; the backward recomputes the (small) attention in torch from the saved inputs."""
+class _AttentionFn(torch.autograd.Function):
+    """Fused tcgen05 attention: native forward (keeps the per-query log-sum-exp) and native backward (two kernels that
+    recompute P).  spatial_n_head must equal n_head when a gate is given (one weight set per head)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, sw, locs, kpm, n_head, spatial_n_head):
+        from . import native
+        out, lse = native.attention(q, k, v, n_head, key_padding_mask=kpm, spatial_w=sw, spatial_heads=spatial_n_head,
+                                    pairwise_locs=locs, return_lse=True)
+        ctx.save_for_backward(q, k, v, out, lse, sw, locs, kpm)
+        ctx.n_head = n_head
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        from . import native
+        q, k, v, out, lse, sw, locs, kpm = ctx.saved_tensors
+        dq, dk, dv, dsw = native.attention_backward(q, k, v, out, grad_out, lse, ctx.n_head, key_padding_mask=kpm,
+                                                    spatial_w=sw, pairwise_locs=locs)
+        return dq, dk, dv, dsw, None, None, None, None
+
+
+class _SpatialAttentionRecomputeFn(torch.autograd.Function):
+    """Native forward, torch-recompute backward: only for a gate shared across heads (spatial_multihead=False)."""
 
     @staticmethod
     def forward(ctx, q, k, v, sw, locs, kpm, n_head, spatial_n_head):
@@ -89,10 +111,12 @@ def attention(q, k, v, num_heads, key_padding_mask=None, dropout_p=0.0):
     key_padding_mask (B,Lk) bool, True = ignore (nn.MultiheadAttention convention)."""
     B, Lq, E = q.shape
     Lk, hd = k.shape[1], E // num_heads
-    if (dropout_p == 0.0 and hd == 64 and Lk <= 160 and _native_ok(q, k, v)
-            and not (torch.is_grad_enabled() and (q.requires_grad or k.requires_grad or v.requires_grad))):
-        from . import native
-        return native.attention(q, k, v, num_heads, key_padding_mask=key_padding_mask)
+    if dropout_p == 0.0 and hd == 64 and Lk <= 160 and _native_ok(q, k, v):
+        if not (torch.is_grad_enabled() and (q.requires_grad or k.requires_grad or v.requires_grad)):
+            from . import native
+            return native.attention(q, k, v, num_heads, key_padding_mask=key_padding_mask)
+        if Lq <= 160:
+            return _AttentionFn.apply(q, k, v, None, None, key_padding_mask, num_heads, 0)
     qh = q.view(B, Lq, num_heads, hd).transpose(1, 2)
     kh = k.view(B, Lk, num_heads, hd).transpose(1, 2)
     vh = v.view(B, Lk, num_heads, hd).transpose(1, 2)
@@ -107,8 +131,8 @@ def spatial_attention(q, k, v, spatial_weights, pairwise_locs, n_head, spatial_n
     """Dispatch: bf16 CUDA tensors with head dim 64 -> fused tcgen05 kernel (attention map not returned: every reference
     caller discards it); anything else -> the torch formulation below."""
     if _native_ok(q, k, v) and q.shape[-1] // n_head == 64 and k.shape[1] <= 160:
-        out = _SpatialAttentionFn.apply(q, k, v, spatial_weights.float(), pairwise_locs.float(), key_padding_mask,
-                                        n_head, spatial_n_head)
+        fn = _AttentionFn if (spatial_n_head == n_head and q.shape[1] <= 160) else _SpatialAttentionRecomputeFn
+        out = fn.apply(q, k, v, spatial_weights.float(), pairwise_locs.float(), key_padding_mask, n_head, spatial_n_head)
         return out, None
     return _spatial_attention_torch(q, k, v, spatial_weights, pairwise_locs, n_head, spatial_n_head, key_padding_mask)
 

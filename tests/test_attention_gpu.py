@@ -61,6 +61,7 @@ def test_spatial_attention_backward_matches_torch():
     locs = ops.calc_pairwise_locs(rand(B, L, 3, seed=6, scale=2.0), None)
     out, attn = ops.spatial_attention(q, k, v, sw, locs, H, H)
     assert attn is None and out.dtype == torch.bfloat16
+    assert isinstance(out.grad_fn, ops._AttentionFn._backward_cls)  # native backward kernels
     out.float().square().sum().backward()
     g_native = [t.grad.clone() for t in (q, k, v, sw)]
     for t in (q, k, v, sw):
@@ -107,3 +108,29 @@ def test_fused_cross_entropy_matches_torch(dtype):
     l2.backward()
     want = torch.nn.functional.cross_entropy(og.detach(), tgt.squeeze(1))
     assert abs(float(l2) - float(want)) < 1e-5 and torch.isfinite(og.grad).all()
+
+
+@pytest.mark.parametrize("Lq,Lk", [(80, 80), (130, 130), (50, 80), (80, 50), (33, 7)])
+def test_plain_attention_backward_native(Lq, Lk):
+    from sceneverse_b200 import ops
+    B, H, E = 3, 12, 768
+    q = rand(B, Lq, E, seed=1).bfloat16().requires_grad_(True)
+    k = rand(B, Lk, E, seed=2).bfloat16().requires_grad_(True)
+    v = rand(B, Lk, E, seed=3).bfloat16().requires_grad_(True)
+    mask = torch.zeros(B, Lk, dtype=torch.bool, device="cuda")
+    mask[1, Lk // 2:] = True
+    go = rand(B, Lq, E, seed=4)
+    out = ops.attention(q, k, v, H, key_padding_mask=mask)              # native forward + native backward
+    assert isinstance(out.grad_fn, ops._AttentionFn._backward_cls)
+    out.backward(go.bfloat16())
+    got = [t.grad.float().clone() for t in (q, k, v)]
+    qf, kf, vf = (t.detach().float().requires_grad_(True) for t in (q, k, v))
+    B_, hd = B, 64
+    qh = qf.view(B, Lq, H, hd).transpose(1, 2); kh = kf.view(B, Lk, H, hd).transpose(1, 2); vh = vf.view(B, Lk, H, hd).transpose(1, 2)
+    att = (qh @ kh.transpose(-1, -2)) * 0.125
+    att = att.masked_fill(mask[:, None, None, :], float("-inf")).softmax(-1)
+    want_out = (att @ vh).transpose(1, 2).reshape(B, Lq, E)
+    want_out.backward(go.bfloat16().float())
+    for g, w, name in zip(got, (qf.grad, kf.grad, vf.grad), "qkv"):
+        err = (g - w).abs().max().item() / (w.abs().max().item() + 1e-9)
+        assert err < 3e-2, (name, err)
