@@ -73,6 +73,21 @@ int sv_attention_bwd_bf16(const void *q, long long q_bs, int q_rs, const void *k
                           const float *lse, int B, int H, int Lq, int Lk, float scale, void *dq, void *dk, void *dv,
                           float *d_spatial_w, float *dvec, void *stream);
 
+/* Dropout variants (nn.MultiheadAttention applies dropout to the attention weights in training, reference
+ * transformers.py:22-24,69-74,118-120): weight (b,h,i,j) is kept iff murmur-fmix64(seed + linear index) >= p * 2^32 and
+ * scaled by 1/(1-p); the backward regenerates the same mask from (dropout_p, seed). */
+int sv_attention_fwd_dropout_bf16(const void *q, long long q_bs, int q_rs, const void *k, long long k_bs, int k_rs,
+                                  const void *v, long long v_bs, int v_rs, void *out, long long o_bs, int o_rs,
+                                  const unsigned char *key_padding_mask, const float *spatial_w, int spatial_heads,
+                                  const float *pairwise_locs, int B, int H, int Lq, int Lk, float scale, float *lse,
+                                  float dropout_p, unsigned long long seed, void *stream);
+int sv_attention_bwd_dropout_bf16(const void *q, long long q_bs, int q_rs, const void *k, long long k_bs, int k_rs,
+                                  const void *v, long long v_bs, int v_rs, const void *o, const void *d_o,
+                                  const unsigned char *key_padding_mask, const float *spatial_w,
+                                  const float *pairwise_locs, const float *lse, int B, int H, int Lq, int Lk, float scale,
+                                  void *dq, void *dk, void *dv, float *d_spatial_w, float *dvec, float dropout_p,
+                                  unsigned long long seed, void *stream);
+
 /* calc_pairwise_locs, 'center' relation (reference: modules/utils.py:38-87): centers (B,O,*) f32 with row stride
  * row_stride (>= 3 floats; xyz first) -> out (B,O,O,5) f32 = [dist/max_dist, dz/dist, dist2d/dist, dy/dist2d, dx/dist2d];
  * dist_norm = 0 keeps the raw distance in slot 0.  eps sits inside the square roots (1e-10 in the reference). */

@@ -14,6 +14,7 @@
 
 #include "svcommon.h"
 #include "svgps.h"
+#include "attn_rng.cuh"
 #include "tc05.cuh"
 
 namespace {
@@ -33,6 +34,9 @@ struct AttnArgs {
   int B, H, SH, Lq, Lk, NKP;       // NKP = Lk rounded up to a multiple of 32
   float scale;
   float *lse;                      // (B,H,Lq) log-sum-exp of the logits per query (for the backward), or null
+  unsigned drop_thresh;            // dropout on the attention weights: keep iff hash >= thresh (0 = off)
+  float inv_keep;                  // 1 / (1 - p)
+  unsigned long long seed;
 };
 
 constexpr int DH = 64;
@@ -191,7 +195,12 @@ __global__ void __launch_bounds__(128, 2) attention_fwd_kernel(const AttnArgs a)
         const float x = gated ? gate[c * 32 + i] : v[i] * a.scale;
         const float p = (on && mx > -INFINITY) ? __expf(x - mx) : 0.f;
         sum += p;
-        v[i] = p;
+        float pd = p;
+        if (a.drop_thresh != 0u) {
+          const unsigned long long idx = (((unsigned long long)b * a.H + h) * a.Lq + qi) * a.Lk + (c * 32 + i);
+          pd = attn_rng::keep(a.seed, idx, a.drop_thresh) ? p * a.inv_keep : 0.f;
+        }
+        v[i] = pd;
       }
       // unnormalised probabilities -> bf16 A operand; 1/sum is applied to the fp32 output row
 #pragma unroll
@@ -280,6 +289,17 @@ extern "C" int sv_attention_fwd_lse_bf16(const void *q, long long q_bs, int q_rs
                                          const unsigned char *key_padding_mask, const float *spatial_w,
                                          int spatial_heads, const float *pairwise_locs, int B, int H, int Lq, int Lk,
                                          float scale, float *lse, void *stream) {
+  return sv_attention_fwd_dropout_bf16(q, q_bs, q_rs, k, k_bs, k_rs, v, v_bs, v_rs, out, o_bs, o_rs, key_padding_mask,
+                                       spatial_w, spatial_heads, pairwise_locs, B, H, Lq, Lk, scale, lse, 0.f, 0ull, stream);
+}
+
+extern "C" int sv_attention_fwd_dropout_bf16(const void *q, long long q_bs, int q_rs, const void *k, long long k_bs,
+                                             int k_rs, const void *v, long long v_bs, int v_rs, void *out, long long o_bs,
+                                             int o_rs, const unsigned char *key_padding_mask, const float *spatial_w,
+                                             int spatial_heads, const float *pairwise_locs, int B, int H, int Lq, int Lk,
+                                             float scale, float *lse, float dropout_p, unsigned long long seed,
+                                             void *stream) {
+  if (dropout_p < 0.f || dropout_p >= 1.f) return SV_ERR_INVALID_ARG;
   if (B < 0 || H < 1 || Lq < 0 || Lk < 1 || Lk > 160) return SV_ERR_INVALID_ARG;
   if (B == 0 || Lq == 0) return SV_OK;
   if (!q || !k || !v || !out) return SV_ERR_INVALID_ARG;
@@ -296,6 +316,9 @@ extern "C" int sv_attention_fwd_lse_bf16(const void *q, long long q_bs, int q_rs
   a.kpm = key_padding_mask; a.sw = spatial_w; a.locs = pairwise_locs;
   a.B = B; a.H = H; a.SH = spatial_heads; a.Lq = Lq; a.Lk = Lk; a.NKP = (Lk + 31) / 32 * 32; a.scale = scale;
   a.lse = lse;
+  a.drop_thresh = dropout_p > 0.f ? (unsigned)((double)dropout_p * 4294967296.0) : 0u;
+  a.inv_keep = 1.0f / (1.0f - dropout_p);
+  a.seed = seed;
   cudaStream_t st = (cudaStream_t)stream;
   switch (a.NKP / 32) {
     case 1: return launch_attn<1>(a, st);

@@ -9,6 +9,7 @@
 
 #include "svcommon.h"
 #include "svgps.h"
+#include "attn_rng.cuh"
 #include "tc05.cuh"
 
 namespace {
@@ -28,6 +29,9 @@ struct BwdArgs {
   __nv_bfloat16 *dq, *dk, *dv;       // contiguous (B,L,H*64)
   float *dsw;                        // (B,Lq,H*6) or null
   float *dvec;                       // (B,H,Lq)
+  unsigned drop_thresh;              // same dropout mask as the forward (0 = off)
+  float inv_keep;
+  unsigned long long seed;
 };
 
 // rows [r0, r0+128) of a (L, *) bf16 matrix (head slice of 64 columns) -> K-major tile [128 x 64]; rows >= L are zero
@@ -171,7 +175,12 @@ __global__ void __launch_bounds__(128, 1) attention_bwd_q_kernel(const BwdArgs a
         float gl = 0.f;
         if (loc != nullptr && j < a.Lk) gl = gate_log(wb, w0, w1, w2, w3, w4, loc + (size_t)j * 5);
         const float p = on ? __expf(s[i] * a.scale + gl - lse) : 0.f;
-        const float ds = p * (dp[i] - D);
+        float dpi = dp[i];
+        if (a.drop_thresh != 0u) {
+          const unsigned long long idx = (((unsigned long long)b * a.H + h) * a.Lq + qi) * a.Lk + j;
+          dpi = attn_rng::keep(a.seed, idx, a.drop_thresh) ? dpi * a.inv_keep : 0.f;
+        }
+        const float ds = p * (dpi - D);
         if (loc != nullptr && on && gl > LOG_CLAMP + 1e-3f) {  // clamp(sigmoid, 1e-6) inactive
           const float dz = ds * (1.0f - __expf(gl));  // d log(sigmoid(z)) / dz = 1 - sigmoid(z)
           const float *l = loc + (size_t)j * 5;
@@ -322,8 +331,15 @@ __global__ void __launch_bounds__(128, 1) attention_bwd_kv_kernel(const BwdArgs 
           }
           p = __expf(s[ii] * a.scale + gl - sLse[i]);
         }
-        s[ii] = p;
-        dp[ii] = p * (dp[ii] - sD[i]) * a.scale;
+        float pd = p, dpi = dp[ii];
+        if (a.drop_thresh != 0u) {
+          const unsigned long long idx = (((unsigned long long)b * a.H + h) * a.Lq + i) * a.Lk + kj;
+          const float m = attn_rng::keep(a.seed, idx, a.drop_thresh) ? a.inv_keep : 0.f;
+          pd = p * m;
+          dpi *= m;
+        }
+        s[ii] = pd;
+        dp[ii] = p * (dpi - sD[i]) * a.scale;
       }
 #pragma unroll
       for (int qd = 0; qd < 4; ++qd) {
@@ -411,6 +427,19 @@ extern "C" int sv_attention_bwd_bf16(const void *q, long long q_bs, int q_rs, co
                                      const float *pairwise_locs, const float *lse, int B, int H, int Lq, int Lk,
                                      float scale, void *dq, void *dk, void *dv, float *d_spatial_w, float *dvec,
                                      void *stream) {
+  return sv_attention_bwd_dropout_bf16(q, q_bs, q_rs, k, k_bs, k_rs, v, v_bs, v_rs, o, d_o, key_padding_mask, spatial_w,
+                                       pairwise_locs, lse, B, H, Lq, Lk, scale, dq, dk, dv, d_spatial_w, dvec, 0.f, 0ull,
+                                       stream);
+}
+
+extern "C" int sv_attention_bwd_dropout_bf16(const void *q, long long q_bs, int q_rs, const void *k, long long k_bs,
+                                             int k_rs, const void *v, long long v_bs, int v_rs, const void *o,
+                                             const void *d_o, const unsigned char *key_padding_mask,
+                                             const float *spatial_w, const float *pairwise_locs, const float *lse, int B,
+                                             int H, int Lq, int Lk, float scale, void *dq, void *dk, void *dv,
+                                             float *d_spatial_w, float *dvec, float dropout_p, unsigned long long seed,
+                                             void *stream) {
+  if (dropout_p < 0.f || dropout_p >= 1.f) return SV_ERR_INVALID_ARG;
   if (B < 0 || H < 1 || Lq < 1 || Lk < 1 || Lq > 160 || Lk > 160) return SV_ERR_INVALID_ARG;
   if (B == 0) return SV_OK;
   if (!q || !k || !v || !o || !d_o || !lse || !dq || !dk || !dv || !dvec) return SV_ERR_INVALID_ARG;
@@ -424,6 +453,9 @@ extern "C" int sv_attention_bwd_bf16(const void *q, long long q_bs, int q_rs, co
   a.B = B; a.H = H; a.Lq = Lq; a.Lk = Lk; a.scale = scale;
   a.dq = (__nv_bfloat16 *)dq; a.dk = (__nv_bfloat16 *)dk; a.dv = (__nv_bfloat16 *)dv;
   a.dsw = d_spatial_w; a.dvec = dvec;
+  a.drop_thresh = dropout_p > 0.f ? (unsigned)((double)dropout_p * 4294967296.0) : 0u;
+  a.inv_keep = 1.0f / (1.0f - dropout_p);
+  a.seed = seed;
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
   switch ((Lk + 31) / 32) {

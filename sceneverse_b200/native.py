@@ -30,7 +30,7 @@ def gemm(a, w, bias=None, act=None, residual=None, out_dtype=torch.bfloat16, row
 
 
 def attention(q, k, v, num_heads, key_padding_mask=None, spatial_w=None, spatial_heads=0, pairwise_locs=None,
-              return_lse=False):
+              return_lse=False, dropout_p=0.0, seed=0):
     """Fused attention forward: q (B,Lq,E), k/v (B,Lk,E) bf16 (views with a contiguous last dim are fine), head dim 64.
     key_padding_mask (B,Lk) bool, True = ignore.  spatial_w (B,Lq,spatial_heads*6) + pairwise_locs (B,Lq,Lk,5) switch on the
     MultiHeadAttentionSpatial 'cond' gate.  Returns (B,Lq,E) bf16."""
@@ -47,17 +47,18 @@ def attention(q, k, v, num_heads, key_padding_mask=None, spatial_w=None, spatial
     lse = torch.empty((B, num_heads, Lq), dtype=torch.float32, device=q.device) if return_lse else None
     lib = _lib.gps()
     with torch.cuda.device(q.device):
-        st = lib.sv_attention_fwd_lse_bf16(
+        st = lib.sv_attention_fwd_dropout_bf16(
             q.data_ptr(), q.stride(0), q.stride(1), k.data_ptr(), k.stride(0), k.stride(1), v.data_ptr(), v.stride(0),
             v.stride(1), out.data_ptr(), out.stride(0), out.stride(1), kpm.data_ptr() if kpm is not None else None,
             sw.data_ptr() if sw is not None else None, int(spatial_heads), locs.data_ptr() if locs is not None else None,
-            B, num_heads, Lq, Lk, 0.125, lse.data_ptr() if lse is not None else None,
+            B, num_heads, Lq, Lk, 0.125, lse.data_ptr() if lse is not None else None, float(dropout_p), int(seed),
             torch.cuda.current_stream(q.device).cuda_stream)
-    _lib.check(lib, st, "sv_attention_fwd_lse_bf16")
+    _lib.check(lib, st, "sv_attention_fwd_dropout_bf16")
     return (out, lse) if return_lse else out
 
 
-def attention_backward(q, k, v, out, grad_out, lse, num_heads, key_padding_mask=None, spatial_w=None, pairwise_locs=None):
+def attention_backward(q, k, v, out, grad_out, lse, num_heads, key_padding_mask=None, spatial_w=None, pairwise_locs=None,
+                       dropout_p=0.0, seed=0):
     """Gradients of `attention` (gate requires one weight set per head).  Returns (dq, dk, dv, d_spatial_w or None)."""
     B, Lq, E = q.shape
     Lk = k.shape[1]
@@ -75,11 +76,12 @@ def attention_backward(q, k, v, out, grad_out, lse, num_heads, key_padding_mask=
         dsw = torch.empty_like(sw)
     lib = _lib.gps()
     with torch.cuda.device(dev):
-        st = lib.sv_attention_bwd_bf16(
+        st = lib.sv_attention_bwd_dropout_bf16(
             q.data_ptr(), q.stride(0), q.stride(1), k.data_ptr(), k.stride(0), k.stride(1), v.data_ptr(), v.stride(0),
             v.stride(1), out.data_ptr(), grad_out.data_ptr(), kpm.data_ptr() if kpm is not None else None,
             sw.data_ptr() if sw is not None else None, locs.data_ptr() if locs is not None else None, lse.data_ptr(),
             B, num_heads, Lq, Lk, 0.125, dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
-            dsw.data_ptr() if dsw is not None else None, dvec.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
-    _lib.check(lib, st, "sv_attention_bwd_bf16")
+            dsw.data_ptr() if dsw is not None else None, dvec.data_ptr(), float(dropout_p), int(seed),
+            torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(lib, st, "sv_attention_bwd_dropout_bf16")
     return dq, dk, dv, dsw

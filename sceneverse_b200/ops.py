@@ -9,10 +9,20 @@ import torch
 import torch.nn.functional as F
 
 NATIVE = {"linear": False,              # plain GEMM -> cuBLAS (library GEMM); fused GEMMs (SA3, fc) use native.gemm
-          "attention": "eval",          # nn.MultiheadAttention core: native tcgen05 kernel when no attention dropout is needed
+          "attention": True,            # nn.MultiheadAttention core incl. attention dropout: native tcgen05 forward + backward
           "spatial_attention": True,    # MultiHeadAttentionSpatial core: native tcgen05 forward and backward
           "calc_pairwise_locs": True,
           "cross_entropy": True}        # masked-LM / grounding CE: fused native forward+gradient
+
+
+_dropout_calls = [0]
+
+
+def _next_dropout_seed():
+    """Deterministic per-call seed of the in-kernel attention dropout: torch's global seed + a call counter (no host
+    sync, CUDA-graph safe); each call then hashes (seed, b, h, i, j)."""
+    _dropout_calls[0] += 1
+    return (torch.initial_seed() * 0x9E3779B1 + _dropout_calls[0] * 0x85EBCA6B) & 0x7FFFFFFFFFFFFFFF
 
 
 def _native_ok(*tensors):
@@ -24,12 +34,12 @@ class _AttentionFn(torch.autograd.Function):
     recompute P).  spatial_n_head must equal n_head when a gate is given (one weight set per head)."""
 
     @staticmethod
-    def forward(ctx, q, k, v, sw, locs, kpm, n_head, spatial_n_head):
+    def forward(ctx, q, k, v, sw, locs, kpm, n_head, spatial_n_head, dropout_p=0.0, seed=0):
         from . import native
         out, lse = native.attention(q, k, v, n_head, key_padding_mask=kpm, spatial_w=sw, spatial_heads=spatial_n_head,
-                                    pairwise_locs=locs, return_lse=True)
+                                    pairwise_locs=locs, return_lse=True, dropout_p=dropout_p, seed=seed)
         ctx.save_for_backward(q, k, v, out, lse, sw, locs, kpm)
-        ctx.n_head = n_head
+        ctx.n_head, ctx.drop = n_head, (dropout_p, seed)
         return out
 
     @staticmethod
@@ -37,8 +47,8 @@ class _AttentionFn(torch.autograd.Function):
         from . import native
         q, k, v, out, lse, sw, locs, kpm = ctx.saved_tensors
         dq, dk, dv, dsw = native.attention_backward(q, k, v, out, grad_out, lse, ctx.n_head, key_padding_mask=kpm,
-                                                    spatial_w=sw, pairwise_locs=locs)
-        return dq, dk, dv, dsw, None, None, None, None
+                                                    spatial_w=sw, pairwise_locs=locs, dropout_p=ctx.drop[0], seed=ctx.drop[1])
+        return dq, dk, dv, dsw, None, None, None, None, None, None
 
 
 class _SpatialAttentionRecomputeFn(torch.autograd.Function):
@@ -111,12 +121,14 @@ def attention(q, k, v, num_heads, key_padding_mask=None, dropout_p=0.0):
     key_padding_mask (B,Lk) bool, True = ignore (nn.MultiheadAttention convention)."""
     B, Lq, E = q.shape
     Lk, hd = k.shape[1], E // num_heads
-    if dropout_p == 0.0 and hd == 64 and Lk <= 160 and _native_ok(q, k, v):
-        if not (torch.is_grad_enabled() and (q.requires_grad or k.requires_grad or v.requires_grad)):
+    if hd == 64 and Lk <= 160 and _native_ok(q, k, v):
+        needs_grad = torch.is_grad_enabled() and (q.requires_grad or k.requires_grad or v.requires_grad)
+        if not needs_grad and dropout_p == 0.0:
             from . import native
             return native.attention(q, k, v, num_heads, key_padding_mask=key_padding_mask)
         if Lq <= 160:
-            return _AttentionFn.apply(q, k, v, None, None, key_padding_mask, num_heads, 0)
+            return _AttentionFn.apply(q, k, v, None, None, key_padding_mask, num_heads, 0, float(dropout_p),
+                                      _next_dropout_seed() if dropout_p > 0.0 else 0)
     qh = q.view(B, Lq, num_heads, hd).transpose(1, 2)
     kh = k.view(B, Lk, num_heads, hd).transpose(1, 2)
     vh = v.view(B, Lk, num_heads, hd).transpose(1, 2)

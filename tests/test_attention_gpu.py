@@ -134,3 +134,40 @@ def test_plain_attention_backward_native(Lq, Lk):
     for g, w, name in zip(got, (qf.grad, kf.grad, vf.grad), "qkv"):
         err = (g - w).abs().max().item() / (w.abs().max().item() + 1e-9)
         assert err < 3e-2, (name, err)
+
+
+def _fmix64_keep(seed, idx, p):
+    import numpy as np
+    x = (idx + np.uint64(seed)).astype(np.uint64)
+    x ^= x >> np.uint64(33)
+    x *= np.uint64(0xff51afd7ed558ccd)
+    x ^= x >> np.uint64(33)
+    x *= np.uint64(0xc4ceb9fe1a85ec53)
+    x ^= x >> np.uint64(33)
+    return (x & np.uint64(0xffffffff)) >= np.uint64(int(p * 4294967296.0))
+
+
+@pytest.mark.parametrize("Lq,Lk", [(130, 130), (80, 50)])
+def test_attention_dropout_forward_backward(Lq, Lk):
+    """Attention-weight dropout inside the kernels: the mask is a pure function of (seed, b, h, i, j), so the torch
+    reference can be fed exactly the same mask."""
+    import numpy as np
+    from sceneverse_b200 import native
+    B, H, E, p, seed = 2, 12, 768, 0.1, 123456789
+    q = rand(B, Lq, E, seed=1).bfloat16(); k = rand(B, Lk, E, seed=2).bfloat16(); v = rand(B, Lk, E, seed=3).bfloat16()
+    go = rand(B, Lq, E, seed=4).bfloat16()
+    out, lse = native.attention(q, k, v, H, return_lse=True, dropout_p=p, seed=seed)
+    dq, dk, dv, _ = native.attention_backward(q, k, v, out, go, lse, H, dropout_p=p, seed=seed)
+    with np.errstate(over="ignore"):
+        idx = np.arange(B * H * Lq * Lk, dtype=np.uint64)
+        keep = torch.from_numpy(_fmix64_keep(seed, idx, p).reshape(B, H, Lq, Lk)).cuda()
+    assert abs(keep.float().mean().item() - (1 - p)) < 0.01
+    qf, kf, vf = (t.float().requires_grad_(True) for t in (q, k, v))
+    qh = qf.view(B, Lq, H, 64).transpose(1, 2); kh = kf.view(B, Lk, H, 64).transpose(1, 2); vh = vf.view(B, Lk, H, 64).transpose(1, 2)
+    att = ((qh @ kh.transpose(-1, -2)) * 0.125).softmax(-1) * keep / (1 - p)
+    want = (att @ vh).transpose(1, 2).reshape(B, Lq, E)
+    want.backward(go.float())
+    assert (out.float() - want).abs().max().item() / want.abs().max().item() < 2e-2
+    for g, w, name in zip((dq, dk, dv), (qf.grad, kf.grad, vf.grad), "qkv"):
+        err = (g.float() - w).abs().max().item() / (w.abs().max().item() + 1e-9)
+        assert err < 3e-2, (name, err)
