@@ -50,7 +50,7 @@ int sv_gemm_bf16(const void *A, int lda, const void *B, int ldb, int M, int N, i
  * [64h, 64h+64).  key_padding_mask (B,Lk) bytes, 1 = ignore (may be NULL).  spatial_w (B,Lq,spatial_heads*6) f32 =
  * [bias, w1..w5] per head and pairwise_locs (B,Lq,Lk,5) f32 enable the MultiHeadAttentionSpatial 'cond' gate
  * log(clamp(sigmoid(w . loc + b), 1e-6)) (reference: modules/layers/transformers.py:206-232); NULL = plain attention
- * (nn.MultiheadAttention core).  Lk <= 160.  out (B,Lq,H*64) bf16. */
+ * (nn.MultiheadAttention core).  Lk <= 256.  out (B,Lq,H*64) bf16. */
 int sv_attention_fwd_bf16(const void *q, long long q_bs, int q_rs, const void *k, long long k_bs, int k_rs,
                           const void *v, long long v_bs, int v_rs, void *out, long long o_bs, int o_rs,
                           const unsigned char *key_padding_mask, const float *spatial_w, int spatial_heads,
@@ -63,10 +63,10 @@ int sv_attention_fwd_lse_bf16(const void *q, long long q_bs, int q_rs, const voi
                               const unsigned char *key_padding_mask, const float *spatial_w, int spatial_heads,
                               const float *pairwise_locs, int B, int H, int Lq, int Lk, float scale, float *lse,
                               void *stream);
-/* Backward of the fused attention (two tcgen05 kernels: dQ + gate-weight gradients with thread == query, dK/dV with
- * thread == key; both recompute P from Q, K, the gate and lse).  q/k/v as in the forward; o, d_o (B,Lq,H*64) bf16
+/* Backward of the fused attention (one tcgen05 kernel template launched twice: dQ + gate-weight gradients with tile rows
+ * == queries, dK/dV with tile rows == keys; both recompute P from Q, K, the gate and lse).  q/k/v as in the forward; o, d_o (B,Lq,H*64) bf16
  * contiguous; dq (B,Lq,H*64), dk, dv (B,Lk,H*64) bf16 contiguous; d_spatial_w (B,Lq,H*6) f32 (NULL without gate; gate
- * requires spatial_heads == H); dvec (B,H,Lq) f32 scratch.  Lq, Lk <= 160. */
+ * requires spatial_heads == H); dvec (B,H,Lq) f32 scratch.  Lq, Lk <= 256. */
 int sv_attention_bwd_bf16(const void *q, long long q_bs, int q_rs, const void *k, long long k_bs, int k_rs,
                           const void *v, long long v_bs, int v_rs, const void *o, const void *d_o,
                           const unsigned char *key_padding_mask, const float *spatial_w, const float *pairwise_locs,
@@ -74,8 +74,10 @@ int sv_attention_bwd_bf16(const void *q, long long q_bs, int q_rs, const void *k
                           float *d_spatial_w, float *dvec, void *stream);
 
 /* Dropout variants (nn.MultiheadAttention applies dropout to the attention weights in training, reference
- * transformers.py:22-24,69-74,118-120): weight (b,h,i,j) is kept iff murmur-fmix64(seed + linear index) >= p * 2^32 and
- * scaled by 1/(1-p); the backward regenerates the same mask from (dropout_p, seed). */
+ * transformers.py:22-24,69-74,118-120): weight (b,h,i,j) is kept iff its 16-bit counter-based uniform (csrc/attn_common.cuh:
+ * one 64-bit mix per (b,h,i) row, one 32-bit mix per key pair) >= round(p * 65536), and scaled by 1/(1-p); the backward
+ * regenerates the same mask from (dropout_p, seed).  Not combinable with the spatial gate (the reference's spatial
+ * attention has no weight dropout). */
 int sv_attention_fwd_dropout_bf16(const void *q, long long q_bs, int q_rs, const void *k, long long k_bs, int k_rs,
                                   const void *v, long long v_bs, int v_rs, void *out, long long o_bs, int o_rs,
                                   const unsigned char *key_padding_mask, const float *spatial_w, int spatial_heads,

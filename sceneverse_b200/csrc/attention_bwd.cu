@@ -1,26 +1,23 @@
-// Backward of the fused attention (csrc/attention.cu) on tcgen05, two kernels per call:
-//   B1 (thread == query row):  S = Q K^T, dP = dO V^T  ->  dS = P o (dP - D)  ->  dQ = scale * dS K,
-//                              gradients of the 6 spatial-gate weights of each (query, head), D = rowsum(dO o O)
-//   B2 (thread == key row):    S^T = K Q^T, dP^T = V dO^T  ->  P^T, dS^T  ->  dV = P^T dO,  dK = scale * dS^T Q
-// P is recomputed from Q, K, the gate and the saved log-sum-exp (no (B,H,L,T) tensor is ever stored).  Every MMA
-// operand is either a row-major (K-major) tile or its explicit transpose staged once in shared memory — the same two
-// operand patterns the forward kernel uses.  Reference math: modules/layers/transformers.py:188-237 (autograd of it).
-#include <cuda_bf16.h>
-
-#include "svcommon.h"
+// Backward of the fused attention (csrc/attention.cu) on tcgen05: ONE kernel template, launched twice per call.
+//   SIDE 0 (tile rows = queries): S = Q K^T, dP = dO V^T -> dS = P o (dP o mask - D) -> dQ = scale * dS K,
+//                                 D = rowsum(dO o O), gradients of the 6 spatial-gate weights of each (query, head)
+//   SIDE 1 (tile rows = keys):    S^T = K Q^T, dP^T = V dO^T -> P^T, dS^T -> dV = (P o mask)^T dO, dK = scale * dS^T Q
+// P is recomputed from Q, K, the gate and the saved log-sum-exp; the dropout mask is regenerated from (seed, indices);
+// no (B,H,L,T) tensor is ever stored.  Reference math: autograd of modules/layers/transformers.py:188-237 and of
+// nn.MultiheadAttention's core (transformers.py:22-24,69-74,118-120).
+// Structure (both sides): the "row" operand pair (Q,dO | K,V) is a 128-row TMA tile, the "column" operand pair
+// (K,V | Q,dO) is staged once per (scene, head); the columns are swept in blocks of 64: two tcgen05.mma chains fill
+// 2 x 64 TMEM columns, the element-wise stage (one thread per row, the two warpgroups split the block's 16-column
+// units) writes the bf16 dS / P tiles, and the output MMAs accumulate over the blocks reading the SAME staged column
+// operand MN-major.  TMEM: 4 x 64 columns, shared memory ~100 KB -> two CTAs per SM.
+#include "attn_common.cuh"
 #include "svgps.h"
-#include "attn_rng.cuh"
-#include "tc05.cuh"
 
 namespace {
 
-using namespace tc05;
-constexpr int DH = 64;
+using namespace attn;
 
 struct BwdArgs {
-  const __nv_bfloat16 *q, *k, *v;
-  long long q_bs, k_bs, v_bs;
-  int q_rs, k_rs, v_rs;
   const __nv_bfloat16 *o, *d_o;      // (B,Lq,H*64) contiguous
   const unsigned char *kpm;          // (B,Lk) or null
   const float *sw, *locs, *lse;      // (B,Lq,H*6) | (B,Lq,Lk,5) | (B,H,Lq)
@@ -28,395 +25,388 @@ struct BwdArgs {
   float scale;
   __nv_bfloat16 *dq, *dk, *dv;       // contiguous (B,L,H*64)
   float *dsw;                        // (B,Lq,H*6) or null
-  float *dvec;                       // (B,H,Lq)
-  unsigned drop_thresh;              // same dropout mask as the forward (0 = off)
+  float *dvec;                       // (B,H,Lq)   D, written by SIDE 0, read by SIDE 1
+  uint32_t t16;
   float inv_keep;
   unsigned long long seed;
 };
 
-// rows [r0, r0+128) of a (L, *) bf16 matrix (head slice of 64 columns) -> K-major tile [128 x 64]; rows >= L are zero
-__device__ __forceinline__ void stage_tile128(uint8_t *dst, const __nv_bfloat16 *base, int row_stride, int r0, int L,
-                                              int tid) {
-  const int r = r0 + tid;
-  const uint4 *src = reinterpret_cast<const uint4 *>(base + (size_t)r * row_stride);
-#pragma unroll
-  for (int c = 0; c < 8; ++c)
-    *reinterpret_cast<uint4 *>(dst + tile_off(128, tid, c * 8)) = r < L ? __ldg(src + c) : make_uint4(0, 0, 0, 0);
-}
-// all L rows (padded to NP) -> natural K-major tile [NP x 64] and / or transposed tile [64 x NP]
-template <bool NAT, bool TR>
-__device__ __forceinline__ void stage_all(uint8_t *nat, uint8_t *tr, const __nv_bfloat16 *base, int row_stride, int L,
-                                          int NP, int tid) {
-  for (int e = tid; e < (NP / 2) * 8; e += 128) {
-    const int jp = e >> 3, c = e & 7, j0 = 2 * jp;
-    uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0;
-    if (j0 < L) a0 = __ldg(reinterpret_cast<const uint4 *>(base + (size_t)j0 * row_stride) + c);
-    if (j0 + 1 < L) a1 = __ldg(reinterpret_cast<const uint4 *>(base + (size_t)(j0 + 1) * row_stride) + c);
-    if (NAT) {
-      *reinterpret_cast<uint4 *>(nat + tile_off(NP, j0, c * 8)) = a0;
-      *reinterpret_cast<uint4 *>(nat + tile_off(NP, j0 + 1, c * 8)) = a1;
-    }
-    if (TR) {
-      const unsigned short *e0 = reinterpret_cast<const unsigned short *>(&a0);
-      const unsigned short *e1 = reinterpret_cast<const unsigned short *>(&a1);
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        *reinterpret_cast<uint32_t *>(tr + tile_off(DH, c * 8 + i, j0)) = (uint32_t)e0[i] | ((uint32_t)e1[i] << 16);
-    }
-  }
-}
-__device__ __forceinline__ float gate_log(float wb, float w0, float w1, float w2, float w3, float w4, const float *l) {
-  const float z = wb + w0 * l[0] + w1 * l[1] + w2 * l[2] + w3 * l[3] + w4 * l[4];
-  return __logf(fmaxf(1.0f / (1.0f + __expf(-z)), 1e-6f));
-}
-constexpr float LOG_CLAMP = -13.815510557964274f;  // log(1e-6)
+__device__ __forceinline__ float u2f(uint32_t x) { return __uint_as_float(x); }
 
-// ------------------------------------------------------------------------------------------------------------------
-// B1: thread == query row
-// ------------------------------------------------------------------------------------------------------------------
-template <int NCH>
-__global__ void __launch_bounds__(128, 1) attention_bwd_q_kernel(const BwdArgs a) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  constexpr int NKP = NCH * 32;
-  uint8_t *sQ = smem;                        // [128 x 64]
-  uint8_t *sdO = sQ + 128 * DH * 2;          // [128 x 64]
-  uint8_t *sK = sdO + 128 * DH * 2;          // [NKP x 64] rows = keys
-  uint8_t *sV = sK + NKP * DH * 2;           // [NKP x 64]
-  uint8_t *sKt = sV + NKP * DH * 2;          // [64 x NKP]
-  uint8_t *sDS = sKt + DH * NKP * 2;         // [128 x NKP]
-  uint64_t *mbar = reinterpret_cast<uint64_t *>(sDS + 128 * NKP * 2);
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(mbar + 1);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
-  const int E = a.H * DH;
-  if (tid == 0) {
-    mbar_init(mbar, 1);
-    mbar_fence_init();
-  }
-  if (warp == 0) tmem_alloc<512>(tmem_slot);
-  stage_all<true, true>(sK, sKt, a.k + (size_t)b * a.k_bs + h * DH, a.k_rs, a.Lk, NKP, tid);
-  stage_all<true, false>(sV, nullptr, a.v + (size_t)b * a.v_bs + h * DH, a.v_rs, a.Lk, NKP, tid);
-  uint32_t kmask[NCH];
-#pragma unroll
-  for (int c = 0; c < NCH; ++c) {
-    const int j = c * 32 + lane;
-    kmask[c] = __ballot_sync(0xffffffffu, j < a.Lk && !(a.kpm && a.kpm[(size_t)b * a.Lk + j]));
-  }
-  fence_before_sync();
-  __syncthreads();
-  fence_after_sync();
-  const uint32_t tmem = *tmem_slot;
-  const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-  constexpr uint32_t COL_S = 0, COL_DP = 160, COL_DQ = 320;
-  uint32_t phase = 0;
-  const bool gated = a.sw != nullptr;
+constexpr uint32_t COL_S = 0, COL_DP = 64, COL_O1 = 128, COL_O2 = 192, TMEM_COLS = 256;
 
-  for (int q0 = 0; q0 < a.Lq; q0 += 128) {
-    const int qi = q0 + tid;
-    const bool qlive = qi < a.Lq;
-    stage_tile128(sQ, a.q + (size_t)b * a.q_bs + h * DH, a.q_rs, q0, a.Lq, tid);
-    stage_tile128(sdO, a.d_o + (size_t)b * a.Lq * E + h * DH, E, q0, a.Lq, tid);
-    // D_i = sum_d dO_id * O_id
-    float D = 0.f;
-    if (qlive) {
-      const uint4 *po = reinterpret_cast<const uint4 *>(a.o + ((size_t)b * a.Lq + qi) * E + h * DH);
-      const uint4 *pd = reinterpret_cast<const uint4 *>(a.d_o + ((size_t)b * a.Lq + qi) * E + h * DH);
+// 64 fp32 accumulator columns of this thread's row -> bf16 row of `dst` (64 contiguous elements)
+__device__ __forceinline__ void store_row64(uint32_t taddr, __nv_bfloat16 *dst, bool live) {
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const uint4 x = __ldg(po + c), y = __ldg(pd + c);
-        const __nv_bfloat162 *xa = reinterpret_cast<const __nv_bfloat162 *>(&x);
-        const __nv_bfloat162 *ya = reinterpret_cast<const __nv_bfloat162 *>(&y);
+  for (int c = 0; c < 2; ++c) {
+    uint32_t r0[16], r1[16];
+    tmem_ld16_async(taddr + c * 32, r0);
+    tmem_ld16_async(taddr + c * 32 + 16, r1);
+    tmem_wait16(r0);
+    tmem_wait16(r1);
+    if (live) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float2 u = __bfloat1622float2(xa[i]), w = __bfloat1622float2(ya[i]);
-          D += u.x * w.x + u.y * w.y;
-        }
-      }
-      a.dvec[((size_t)b * a.H + h) * a.Lq + qi] = D;
-    }
-    fence_proxy_async_smem();
-    fence_before_sync();
-    __syncthreads();
-    if (tid == 0) {
-      fence_after_sync();
-      const uint32_t idesc = make_idesc_bf16(128, NKP);
-      const uint32_t aQ = smem_u32(sQ), aO = smem_u32(sdO), aK = smem_u32(sK), aV = smem_u32(sV);
-#pragma unroll
-      for (int ks = 0; ks < DH / 16; ++ks)
-        mma_bf16(tmem + COL_S, make_desc(aQ + ks * 4096, 2048, 128), make_desc(aK + ks * 2 * (NKP * 16), NKP * 16, 128),
-                 idesc, ks > 0);
-#pragma unroll
-      for (int ks = 0; ks < DH / 16; ++ks)
-        mma_bf16(tmem + COL_DP, make_desc(aO + ks * 4096, 2048, 128), make_desc(aV + ks * 2 * (NKP * 16), NKP * 16, 128),
-                 idesc, ks > 0);
-      mma_commit(mbar);
-    }
-    float wb = 0.f, w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f, w4 = 0.f;
-    const float *loc = nullptr;
-    if (gated && qlive) {
-      const float *w = a.sw + ((size_t)b * a.Lq + qi) * (a.H * 6) + h * 6;
-      wb = w[0]; w0 = w[1]; w1 = w[2]; w2 = w[3]; w3 = w[4]; w4 = w[5];
-      loc = a.locs + ((size_t)b * a.Lq + qi) * (size_t)a.Lk * 5;
-    }
-    const float lse = qlive ? a.lse[((size_t)b * a.H + h) * a.Lq + qi] : INFINITY;
-    mbar_wait(mbar, phase);
-    phase ^= 1u;
-    fence_after_sync();
-    float gb = 0.f, g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f, g4 = 0.f;
-#pragma unroll 1
-    for (int c = 0; c < NCH; ++c) {
-      float s[32], dp[32];
-      tmem_ld32(trow + COL_S + c * 32, s);
-      tmem_ld32(trow + COL_DP + c * 32, dp);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const int j = c * 32 + i;
-        const bool on = ((kmask[c] >> i) & 1u) && qlive;
-        float gl = 0.f;
-        if (loc != nullptr && j < a.Lk) gl = gate_log(wb, w0, w1, w2, w3, w4, loc + (size_t)j * 5);
-        const float p = on ? __expf(s[i] * a.scale + gl - lse) : 0.f;
-        float dpi = dp[i];
-        if (a.drop_thresh != 0u) {
-          const unsigned long long idx = (((unsigned long long)b * a.H + h) * a.Lq + qi) * a.Lk + j;
-          dpi = attn_rng::keep(a.seed, idx, a.drop_thresh) ? dpi * a.inv_keep : 0.f;
-        }
-        const float ds = p * (dpi - D);
-        if (loc != nullptr && on && gl > LOG_CLAMP + 1e-3f) {  // clamp(sigmoid, 1e-6) inactive
-          const float dz = ds * (1.0f - __expf(gl));  // d log(sigmoid(z)) / dz = 1 - sigmoid(z)
-          const float *l = loc + (size_t)j * 5;
-          gb += dz; g0 += dz * l[0]; g1 += dz * l[1]; g2 += dz * l[2]; g3 += dz * l[3]; g4 += dz * l[4];
-        }
-        s[i] = ds * a.scale;
-      }
-#pragma unroll
-      for (int qd = 0; qd < 4; ++qd) {
-        uint32_t w[4];
-#pragma unroll
-        for (int hh = 0; hh < 4; ++hh) w[hh] = pack_bf16(s[qd * 8 + hh * 2], s[qd * 8 + hh * 2 + 1]);
-        *reinterpret_cast<uint4 *>(sDS + tile_off(128, tid, c * 32 + qd * 8)) = make_uint4(w[0], w[1], w[2], w[3]);
-      }
-    }
-    if (a.dsw != nullptr && qlive) {
-      float *g = a.dsw + ((size_t)b * a.Lq + qi) * (a.H * 6) + h * 6;
-      g[0] = gb; g[1] = g0; g[2] = g1; g[3] = g2; g[4] = g3; g[5] = g4;
-    }
-    fence_proxy_async_smem();
-    fence_before_sync();
-    __syncthreads();
-    if (tid == 0) {
-      fence_after_sync();
-      const uint32_t idesc = make_idesc_bf16(128, DH);
-      const uint32_t aS = smem_u32(sDS), aT = smem_u32(sKt);
-#pragma unroll
-      for (int ks = 0; ks < NKP / 16; ++ks)
-        mma_bf16(tmem + COL_DQ, make_desc(aS + ks * 4096, 2048, 128), make_desc(aT + ks * 2 * (DH * 16), DH * 16, 128), idesc,
-                 ks > 0);
-      mma_commit(mbar);
-    }
-    mbar_wait(mbar, phase);
-    phase ^= 1u;
-    fence_after_sync();
-    {
-      __nv_bfloat16 *o = a.dq + ((size_t)b * a.Lq + qi) * E + h * DH;
-#pragma unroll
-      for (int c0 = 0; c0 < DH; c0 += 32) {
-        float v[32];
-        tmem_ld32(trow + COL_DQ + c0, v);
-        if (qlive) {
-#pragma unroll
-          for (int qd = 0; qd < 4; ++qd) {
-            uint32_t w[4];
-#pragma unroll
-            for (int hh = 0; hh < 4; ++hh) w[hh] = pack_bf16(v[qd * 8 + hh * 2], v[qd * 8 + hh * 2 + 1]);
-            *reinterpret_cast<uint4 *>(o + c0 + qd * 8) = make_uint4(w[0], w[1], w[2], w[3]);
-          }
-        }
-      }
-    }
-    fence_before_sync();
-  }
-  fence_before_sync();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc<512>(tmem);
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// B2: thread == key row
-// ------------------------------------------------------------------------------------------------------------------
-template <int NQCH>
-__global__ void __launch_bounds__(128, 1) attention_bwd_kv_kernel(const BwdArgs a) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  constexpr int NQP = NQCH * 32;
-  uint8_t *sKr = smem;                        // [128 x 64]  rows = keys of this tile
-  uint8_t *sVr = sKr + 128 * DH * 2;          // [128 x 64]
-  uint8_t *sQn = sVr + 128 * DH * 2;          // [NQP x 64]  rows = queries
-  uint8_t *sOn = sQn + NQP * DH * 2;          // [NQP x 64]  dO
-  uint8_t *sQt = sOn + NQP * DH * 2;          // [64 x NQP]
-  uint8_t *sOt = sQt + DH * NQP * 2;          // [64 x NQP]  dO^T
-  uint8_t *sPT = sOt + DH * NQP * 2;          // [128 x NQP] P^T
-  uint8_t *sDST = sPT + 128 * NQP * 2;        // [128 x NQP] scale * dS^T
-  float *sLse = reinterpret_cast<float *>(sDST + 128 * NQP * 2);  // [NQP]
-  float *sD = sLse + NQP;                                          // [NQP]
-  float *sW = sD + NQP;                                            // [NQP][6]
-  uint64_t *mbar = reinterpret_cast<uint64_t *>(sW + NQP * 6);
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(mbar + 1);
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
-  const int E = a.H * DH;
-  if (tid == 0) {
-    mbar_init(mbar, 1);
-    mbar_fence_init();
-  }
-  if (warp == 0) tmem_alloc<512>(tmem_slot);
-  stage_all<true, true>(sQn, sQt, a.q + (size_t)b * a.q_bs + h * DH, a.q_rs, a.Lq, NQP, tid);
-  stage_all<true, true>(sOn, sOt, a.d_o + (size_t)b * a.Lq * E + h * DH, E, a.Lq, NQP, tid);
-  const bool gated = a.sw != nullptr;
-  for (int i = tid; i < NQP; i += 128) {
-    const bool live = i < a.Lq;
-    sLse[i] = live ? a.lse[((size_t)b * a.H + h) * a.Lq + i] : INFINITY;
-    sD[i] = live ? a.dvec[((size_t)b * a.H + h) * a.Lq + i] : 0.f;
-    if (gated) {
-      const float *w = a.sw + ((size_t)b * a.Lq + (live ? i : 0)) * (a.H * 6) + h * 6;
-#pragma unroll
-      for (int t = 0; t < 6; ++t) sW[i * 6 + t] = live ? w[t] : 0.f;
-    }
-  }
-  fence_before_sync();
-  __syncthreads();
-  fence_after_sync();
-  const uint32_t tmem = *tmem_slot;
-  const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-  constexpr uint32_t COL_ST = 0, COL_DPT = 160, COL_DV = 320, COL_DK = 384;
-  uint32_t phase = 0;
-
-  for (int k0 = 0; k0 < a.Lk; k0 += 128) {
-    const int kj = k0 + tid;
-    const bool klive = kj < a.Lk && !(a.kpm && a.kpm[(size_t)b * a.Lk + kj]);
-    stage_tile128(sKr, a.k + (size_t)b * a.k_bs + h * DH, a.k_rs, k0, a.Lk, tid);
-    stage_tile128(sVr, a.v + (size_t)b * a.v_bs + h * DH, a.v_rs, k0, a.Lk, tid);
-    fence_proxy_async_smem();
-    fence_before_sync();
-    __syncthreads();
-    if (tid == 0) {
-      fence_after_sync();
-      const uint32_t idesc = make_idesc_bf16(128, NQP);
-      const uint32_t aK = smem_u32(sKr), aV = smem_u32(sVr), aQ = smem_u32(sQn), aO = smem_u32(sOn);
-#pragma unroll
-      for (int ks = 0; ks < DH / 16; ++ks)
-        mma_bf16(tmem + COL_ST, make_desc(aK + ks * 4096, 2048, 128), make_desc(aQ + ks * 2 * (NQP * 16), NQP * 16, 128),
-                 idesc, ks > 0);
-#pragma unroll
-      for (int ks = 0; ks < DH / 16; ++ks)
-        mma_bf16(tmem + COL_DPT, make_desc(aV + ks * 4096, 2048, 128), make_desc(aO + ks * 2 * (NQP * 16), NQP * 16, 128),
-                 idesc, ks > 0);
-      mma_commit(mbar);
-    }
-    mbar_wait(mbar, phase);
-    phase ^= 1u;
-    fence_after_sync();
-#pragma unroll 1
-    for (int c = 0; c < NQCH; ++c) {
-      float s[32], dp[32];
-      tmem_ld32(trow + COL_ST + c * 32, s);
-      tmem_ld32(trow + COL_DPT + c * 32, dp);
-#pragma unroll
-      for (int ii = 0; ii < 32; ++ii) {
-        const int i = c * 32 + ii;  // query
-        float p = 0.f;
-        if (klive && i < a.Lq) {
-          float gl = 0.f;
-          if (gated) {
-            const float *w = sW + i * 6;
-            gl = gate_log(w[0], w[1], w[2], w[3], w[4], w[5], a.locs + (((size_t)b * a.Lq + i) * a.Lk + kj) * 5);
-          }
-          p = __expf(s[ii] * a.scale + gl - sLse[i]);
-        }
-        float pd = p, dpi = dp[ii];
-        if (a.drop_thresh != 0u) {
-          const unsigned long long idx = (((unsigned long long)b * a.H + h) * a.Lq + i) * a.Lk + kj;
-          const float m = attn_rng::keep(a.seed, idx, a.drop_thresh) ? a.inv_keep : 0.f;
-          pd = p * m;
-          dpi *= m;
-        }
-        s[ii] = pd;
-        dp[ii] = p * (dpi - sD[i]) * a.scale;
-      }
-#pragma unroll
-      for (int qd = 0; qd < 4; ++qd) {
+      for (int hf = 0; hf < 2; ++hf) {
         uint32_t w[4], z[4];
 #pragma unroll
-        for (int hh = 0; hh < 4; ++hh) {
-          w[hh] = pack_bf16(s[qd * 8 + hh * 2], s[qd * 8 + hh * 2 + 1]);
-          z[hh] = pack_bf16(dp[qd * 8 + hh * 2], dp[qd * 8 + hh * 2 + 1]);
+        for (int e = 0; e < 4; ++e) {
+          w[e] = pack_bf16(u2f(r0[hf * 8 + e * 2]), u2f(r0[hf * 8 + e * 2 + 1]));
+          z[e] = pack_bf16(u2f(r1[hf * 8 + e * 2]), u2f(r1[hf * 8 + e * 2 + 1]));
         }
-        *reinterpret_cast<uint4 *>(sPT + tile_off(128, tid, c * 32 + qd * 8)) = make_uint4(w[0], w[1], w[2], w[3]);
-        *reinterpret_cast<uint4 *>(sDST + tile_off(128, tid, c * 32 + qd * 8)) = make_uint4(z[0], z[1], z[2], z[3]);
+        *reinterpret_cast<uint4 *>(dst + c * 32 + hf * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4 *>(dst + c * 32 + 16 + hf * 8) = make_uint4(z[0], z[1], z[2], z[3]);
       }
     }
-    fence_proxy_async_smem();
-    fence_before_sync();
-    __syncthreads();
-    if (tid == 0) {
-      fence_after_sync();
-      const uint32_t idesc = make_idesc_bf16(128, DH);
-      const uint32_t aP = smem_u32(sPT), aS = smem_u32(sDST), aOt = smem_u32(sOt), aQt = smem_u32(sQt);
+  }
+}
+
+template <int SIDE, bool GATED, bool DROP>
+__global__ void __launch_bounds__(256, 2)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap mR1, const __grid_constant__ CUtensorMap mR2,
+                const __grid_constant__ CUtensorMap mC1, const __grid_constant__ CUtensorMap mC2, const BwdArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int Lr = SIDE == 0 ? a.Lq : a.Lk;    // rows of the tiles
+  const int Lc = SIDE == 0 ? a.Lk : a.Lq;    // columns swept in blocks of 64
+  const int NC = (Lc + 15) & ~15;
+  uint8_t *sR1 = smem;                       // [128][64] sw128   Q  | K
+  uint8_t *sR2 = sR1 + 16384;                // [128][64] sw128   dO | V
+  uint8_t *sC1 = sR2 + 16384;                // [NC][64]  sw128   K  | Q
+  uint8_t *sC2 = sC1 + NC * 128;             // [NC][64]  sw128   V  | dO
+  uint8_t *sG1 = sC2 + NC * 128;             // [8][128][8] K-major   scale * dS (^T)
+  uint8_t *sG2 = sG1 + 16384;                // [8][128][8] K-major   dropped P^T (SIDE 1)
+  float *vec = reinterpret_cast<float *>(sG2 + (SIDE == 1 ? 16384 : 0));
+  // SIDE 0: vec = kb[NC] | red[128][6] (GATED)      SIDE 1: vec = lse2[NC] | Dv[NC] | rk[NC] | W[NC][6] (GATED)
+  float *kb = vec, *red = vec + NC;
+  float *lse2s = vec, *Dv = vec + NC;
+  uint32_t *rks = reinterpret_cast<uint32_t *>(vec + 2 * NC);
+  float *Ws = vec + 3 * NC;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(vec + (SIDE == 0 ? NC + 768 : 9 * NC));  // 0: C landed, 1: R tile, 2: MMA
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wg = warp >> 2, wq = warp & 3;
+  const int row = wq * 32 + lane;
+  const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
+  const int E = a.H * DH;
+
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_init(&bars[2], 1);
+    mbar_fence_init();
+    tma_prefetch_desc(&mR1);
+    tma_prefetch_desc(&mR2);
+    tma_prefetch_desc(&mC1);
+    tma_prefetch_desc(&mC2);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&bars[0], 2 * rows_bytes(0, NC >> 4, Lc));
+    tma_rows(sC1, &mC1, h, 0, NC >> 4, Lc, b, &bars[0]);
+    tma_rows(sC2, &mC2, h, 0, NC >> 4, Lc, b, &bars[0]);
+    mbar_expect_tx(&bars[1], 2 * rows_bytes(0, 8, Lr));
+    tma_rows(sR1, &mR1, h, 0, 8, Lr, b, &bars[1]);
+    tma_rows(sR2, &mR2, h, 0, 8, Lr, b, &bars[1]);
+  }
+  if (warp == 1) tmem_alloc_n(tmem_slot, TMEM_COLS);
+  // per-column vectors
+  for (int c = tid; c < NC; c += 256) {
+    if (SIDE == 0) {
+      kb[c] = (c < a.Lk && !(a.kpm != nullptr && a.kpm[(size_t)b * a.Lk + c])) ? 0.f : -INFINITY;
+    } else {
+      const bool live = c < a.Lq;
+      const size_t r = ((size_t)b * a.H + h) * a.Lq + c;
+      lse2s[c] = live ? a.lse[r] * LOG2E : INFINITY;
+      Dv[c] = live ? a.dvec[r] : 0.f;
+      rks[c] = DROP ? drop_row_key(a.seed, r) : 0u;
+      if (GATED) {
+        const float *w = a.sw + ((size_t)b * a.Lq + (live ? c : 0)) * (a.H * 6) + h * 6;
 #pragma unroll
-      for (int ks = 0; ks < NQP / 16; ++ks)
-        mma_bf16(tmem + COL_DV, make_desc(aP + ks * 4096, 2048, 128), make_desc(aOt + ks * 2 * (DH * 16), DH * 16, 128), idesc,
-                 ks > 0);
-#pragma unroll
-      for (int ks = 0; ks < NQP / 16; ++ks)
-        mma_bf16(tmem + COL_DK, make_desc(aS + ks * 4096, 2048, 128), make_desc(aQt + ks * 2 * (DH * 16), DH * 16, 128), idesc,
-                 ks > 0);
-      mma_commit(mbar);
-    }
-    mbar_wait(mbar, phase);
-    phase ^= 1u;
-    fence_after_sync();
-#pragma unroll
-    for (int which = 0; which < 2; ++which) {
-      __nv_bfloat16 *o = (which ? a.dk : a.dv) + ((size_t)b * a.Lk + kj) * E + h * DH;
-#pragma unroll
-      for (int c0 = 0; c0 < DH; c0 += 32) {
-        float v[32];
-        tmem_ld32(trow + (which ? COL_DK : COL_DV) + c0, v);
-        if (kj < a.Lk) {
-#pragma unroll
-          for (int qd = 0; qd < 4; ++qd) {
-            uint32_t w[4];
-#pragma unroll
-            for (int hh = 0; hh < 4; ++hh) w[hh] = pack_bf16(v[qd * 8 + hh * 2], v[qd * 8 + hh * 2 + 1]);
-            *reinterpret_cast<uint4 *>(o + c0 + qd * 8) = make_uint4(w[0], w[1], w[2], w[3]);
-          }
-        }
+        for (int t = 0; t < 6; ++t) Ws[c * 6 + t] = live ? -LOG2E * w[t] : 0.f;
       }
     }
-    fence_before_sync();
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 0) tmem_dealloc<512>(tmem);
+  fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t trow = tmem + ((uint32_t)(wq * 32) << 16);
+  const float c2 = a.scale * LOG2E;
+  const int nblk = (NC + 63) >> 6;
+  uint32_t ph_r = 0, ph_m = 0;
+
+  for (int r0 = 0; r0 < Lr; r0 += 128) {
+    const int ri = r0 + row;                     // query (SIDE 0) / key (SIDE 1) of this thread
+    const bool rlive = ri < Lr;
+    const bool wlive = r0 + wq * 32 < Lr;        // warp-uniform
+    // ---- per-row state ------------------------------------------------------------------------------------------------
+    float lse2 = INFINITY, D = 0.f;              // SIDE 0
+    GateW gw;
+    const float *loc = nullptr;
+    uint32_t rk = 0;
+    bool klive = false;                          // SIDE 1: key takes part
+    float gb = 0.f, g0 = 0.f, g1 = 0.f, g2a = 0.f, g3 = 0.f, g4 = 0.f;
+    if (SIDE == 0) {
+      if (rlive) {
+        const size_t r = ((size_t)b * a.H + h) * a.Lq + ri;
+        lse2 = a.lse[r] * LOG2E;
+        const uint4 *po = reinterpret_cast<const uint4 *>(a.o + ((size_t)b * a.Lq + ri) * E + h * DH);
+        const uint4 *pd = reinterpret_cast<const uint4 *>(a.d_o + ((size_t)b * a.Lq + ri) * E + h * DH);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 x = __ldg(po + c), y = __ldg(pd + c);
+          const __nv_bfloat162 *xa = reinterpret_cast<const __nv_bfloat162 *>(&x);
+          const __nv_bfloat162 *ya = reinterpret_cast<const __nv_bfloat162 *>(&y);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 u = __bfloat1622float2(xa[i]), w = __bfloat1622float2(ya[i]);
+            D = fmaf(u.x, w.x, fmaf(u.y, w.y, D));
+          }
+        }
+        if (wg == 0) a.dvec[r] = D;
+        if (GATED) {
+          gw.load(a.sw + ((size_t)b * a.Lq + ri) * (a.H * 6) + h * 6);
+          loc = a.locs + ((size_t)b * a.Lq + ri) * (size_t)a.Lk * 5;
+        }
+        if (DROP) rk = drop_row_key(a.seed, r);
+      }
+    } else {
+      klive = rlive && !(a.kpm != nullptr && a.kpm[(size_t)b * a.Lk + ri]);
+    }
+    const bool vec_loc = SIDE == 0 && GATED && (a.Lk & 3) == 0;
+
+    for (int blk = 0; blk < nblk; ++blk) {
+      const int nb = min(64, NC - blk * 64);     // columns of this block (multiple of 16)
+      // ---- S_blk, dP_blk ---------------------------------------------------------------------------------------------
+      if (tid == 0) {
+        if (blk == 0) {
+          if (r0 == 0) mbar_wait(&bars[0], 0);
+          mbar_wait(&bars[1], ph_r);
+        }
+        fence_after_sync();
+        const uint32_t aR1 = smem_u32(sR1), aR2 = smem_u32(sR2);
+        const uint32_t aC1 = smem_u32(sC1) + blk * 8192, aC2 = smem_u32(sC2) + blk * 8192;
+        const uint32_t idesc = idesc_kk(nb);
+#pragma unroll
+        for (int ks = 0; ks < DH / 16; ++ks)
+          mma_bf16(tmem + COL_S, make_desc_sw128(aR1 + ks * 32), make_desc_sw128(aC1 + ks * 32), idesc, ks > 0);
+#pragma unroll
+        for (int ks = 0; ks < DH / 16; ++ks)
+          mma_bf16(tmem + COL_DP, make_desc_sw128(aR2 + ks * 32), make_desc_sw128(aC2 + ks * 32), idesc, ks > 0);
+        mma_commit(&bars[2]);
+      }
+      mbar_wait(&bars[2], ph_m);
+      ph_m ^= 1u;
+      fence_after_sync();
+      if (tid == 0 && blk == nblk - 1 && r0 + 128 < Lr) {  // row operands are free: fetch the next tile
+        mbar_expect_tx(&bars[1], 2 * rows_bytes(r0 + 128, 8, Lr));
+        tma_rows(sR1, &mR1, h, r0 + 128, 8, Lr, b, &bars[1]);
+        tma_rows(sR2, &mR2, h, r0 + 128, 8, Lr, b, &bars[1]);
+      }
+
+      // ---- element-wise stage: 16-column units, alternating between the warpgroups ----------------------------------------
+      if (wlive) {
+#pragma unroll 1
+        for (int u = (wg + blk) & 1; u < (nb >> 4); u += 2) {
+          const int cl = u * 16;                 // column inside the block
+          const int c0 = blk * 64 + cl;          // global column (key for SIDE 0, query for SIDE 1)
+          uint32_t rs[16], rd[16];
+          tmem_ld16_async(trow + COL_S + cl, rs);
+          tmem_ld16_async(trow + COL_DP + cl, rd);
+          float gl[16];
+          if (GATED) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) gl[i] = 0.f;
+            if (SIDE == 0) {
+              if (loc != nullptr) {
+                if (vec_loc) {
+                  const float4 *l4 = reinterpret_cast<const float4 *>(loc + (size_t)c0 * 5);
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    if (c0 + q * 4 < a.Lk) {
+                      const float4 A = __ldg(l4 + q * 5), B2 = __ldg(l4 + q * 5 + 1), C = __ldg(l4 + q * 5 + 2),
+                                   Dd = __ldg(l4 + q * 5 + 3), Ee = __ldg(l4 + q * 5 + 4);
+                      gl[q * 4] = gw.log2gate(A.x, A.y, A.z, A.w, B2.x);
+                      gl[q * 4 + 1] = gw.log2gate(B2.y, B2.z, B2.w, C.x, C.y);
+                      gl[q * 4 + 2] = gw.log2gate(C.z, C.w, Dd.x, Dd.y, Dd.z);
+                      gl[q * 4 + 3] = gw.log2gate(Dd.w, Ee.x, Ee.y, Ee.z, Ee.w);
+                    }
+                  }
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i)
+                    if (c0 + i < a.Lk) {
+                      const float *l = loc + (size_t)(c0 + i) * 5;
+                      gl[i] = gw.log2gate(l[0], l[1], l[2], l[3], l[4]);
+                    }
+                }
+              }
+            } else if (klive) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (c0 + i < a.Lq) {
+                  const float *w = Ws + (c0 + i) * 6;
+                  const GateW g{w[0], w[1], w[2], w[3], w[4], w[5]};
+                  const float *l = a.locs + (((size_t)b * a.Lq + c0 + i) * a.Lk + ri) * 5;
+                  gl[i] = g.log2gate(__ldg(l), __ldg(l + 1), __ldg(l + 2), __ldg(l + 3), __ldg(l + 4));
+                }
+            }
+          }
+          tmem_wait16(rs);
+          tmem_wait16(rd);
+          float ds[16], pd[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float p, dpi = u2f(rd[i]);
+            if (SIDE == 0) {
+              float x = fmaf(u2f(rs[i]), c2, kb[c0 + i]) - lse2;
+              if (GATED) x += gl[i];
+              p = ex2f(x);
+            } else {
+              float x = fmaf(u2f(rs[i]), c2, -lse2s[c0 + i]);
+              if (GATED) x += gl[i];
+              p = klive ? ex2f(x) : 0.f;
+            }
+            float m = 1.f;
+            if (DROP) {
+              const uint32_t hh = SIDE == 0 ? drop_pair_hash(rk, (uint32_t)(c0 + i) >> 1)
+                                            : drop_pair_hash(rks[c0 + i], (uint32_t)ri >> 1);
+              m = drop_keep(hh, SIDE == 0 ? (uint32_t)(c0 + i) : (uint32_t)ri, a.t16) ? a.inv_keep : 0.f;
+              dpi *= m;
+            }
+            const float dsi = p * (dpi - (SIDE == 0 ? D : Dv[c0 + i]));
+            if (SIDE == 0 && GATED) {
+              if (gl[i] > LOG2_CLAMP && c0 + i < a.Lk && loc != nullptr) {  // clamp(sigmoid, 1e-6) inactive
+                const float dz = dsi * (1.0f - ex2f(gl[i]));                // d log(sigmoid(z)) / dz = 1 - sigmoid(z)
+                const float *l = loc + (size_t)(c0 + i) * 5;
+                gb += dz;
+                g0 = fmaf(dz, __ldg(l), g0);
+                g1 = fmaf(dz, __ldg(l + 1), g1);
+                g2a = fmaf(dz, __ldg(l + 2), g2a);
+                g3 = fmaf(dz, __ldg(l + 3), g3);
+                g4 = fmaf(dz, __ldg(l + 4), g4);
+              }
+            }
+            ds[i] = dsi * a.scale;
+            pd[i] = p * m;
+          }
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) w[e] = pack_bf16(ds[hf * 8 + e * 2], ds[hf * 8 + e * 2 + 1]);
+            *reinterpret_cast<uint4 *>(sG1 + tile_off(128, row, cl + hf * 8)) = make_uint4(w[0], w[1], w[2], w[3]);
+            if (SIDE == 1) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) w[e] = pack_bf16(pd[hf * 8 + e * 2], pd[hf * 8 + e * 2 + 1]);
+              *reinterpret_cast<uint4 *>(sG2 + tile_off(128, row, cl + hf * 8)) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+          }
+        }
+      }
+      if (SIDE == 0 && GATED && blk == nblk - 1 && wg == 1) {
+        float *r = red + row * 6;
+        r[0] = gb; r[1] = g0; r[2] = g1; r[3] = g2a; r[4] = g3; r[5] = g4;
+      }
+      fence_proxy_async_smem();
+      fence_before_sync();
+      __syncthreads();
+
+      // ---- accumulate the outputs over this block's columns (column operand read MN-major) -------------------------------
+      if (tid == 0) {
+        fence_after_sync();
+        const uint32_t aG1 = smem_u32(sG1), aG2 = smem_u32(sG2);
+        const uint32_t aC1 = smem_u32(sC1) + blk * 8192, aC2 = smem_u32(sC2) + blk * 8192;
+        const uint32_t idesc = idesc_kmn(DH);
+#pragma unroll 1
+        for (int ks = 0; ks < (nb >> 4); ++ks) {
+          mma_bf16(tmem + COL_O1, make_desc(aG1 + ks * 4096, 2048, 128), make_desc_sw128_mn(aC1 + ks * 2048), idesc,
+                   (blk | ks) != 0);
+          if (SIDE == 1)
+            mma_bf16(tmem + COL_O2, make_desc(aG2 + ks * 4096, 2048, 128), make_desc_sw128_mn(aC2 + ks * 2048), idesc,
+                     (blk | ks) != 0);
+        }
+        if (blk == nblk - 1) mma_commit(&bars[2]);
+      }
+    }
+    mbar_wait(&bars[2], ph_m);
+    ph_m ^= 1u;
+    fence_after_sync();
+    ph_r ^= 1u;
+
+    // ---- epilogue ----------------------------------------------------------------------------------------------------------
+    if (wlive) {
+      if (SIDE == 0) {
+        // dQ: each warpgroup stores 32 of the 64 columns
+        uint32_t q0[16], q1[16];
+        tmem_ld16_async(trow + COL_O1 + wg * 32, q0);
+        tmem_ld16_async(trow + COL_O1 + wg * 32 + 16, q1);
+        tmem_wait16(q0);
+        tmem_wait16(q1);
+        if (rlive) {
+          __nv_bfloat16 *o = a.dq + ((size_t)b * a.Lq + ri) * E + h * DH + wg * 32;
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            uint32_t w[4], z[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              w[e] = pack_bf16(u2f(q0[hf * 8 + e * 2]), u2f(q0[hf * 8 + e * 2 + 1]));
+              z[e] = pack_bf16(u2f(q1[hf * 8 + e * 2]), u2f(q1[hf * 8 + e * 2 + 1]));
+            }
+            *reinterpret_cast<uint4 *>(o + hf * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4 *>(o + 16 + hf * 8) = make_uint4(z[0], z[1], z[2], z[3]);
+          }
+          if (GATED && wg == 0 && a.dsw != nullptr) {
+            const float *r = red + row * 6;
+            float *g = a.dsw + ((size_t)b * a.Lq + ri) * (a.H * 6) + h * 6;
+            g[0] = gb + r[0]; g[1] = g0 + r[1]; g[2] = g1 + r[2]; g[3] = g2a + r[3]; g[4] = g3 + r[4]; g[5] = g4 + r[5];
+          }
+        }
+      } else {
+        // warpgroup 0 stores dV (from the dropped P^T), warpgroup 1 stores dK (from scale * dS^T)
+        __nv_bfloat16 *o = (wg == 0 ? a.dv : a.dk) + ((size_t)b * a.Lk + ri) * E + h * DH;
+        store_row64(trow + (wg == 0 ? COL_O2 : COL_O1), o, rlive);
+      }
+    }
+    if (r0 + 128 < Lr) {
+      fence_before_sync();
+      __syncthreads();
+      fence_after_sync();
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc_n(tmem, TMEM_COLS);
 }
 
-template <int NCH>
-int launch_q(const BwdArgs &a, cudaStream_t st) {
-  constexpr int NKP = NCH * 32;
-  constexpr size_t smem = (size_t)2 * 128 * DH * 2 + (size_t)3 * NKP * DH * 2 + (size_t)128 * NKP * 2 + 32;
-  auto kern = attention_bwd_q_kernel<NCH>;
-  int rc = sv::cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (rc) return rc;
-  kern<<<a.B * a.H, 128, smem, st>>>(a);
+template <int SIDE, bool GATED, bool DROP>
+int launch_side(const CUtensorMap &r1, const CUtensorMap &r2, const CUtensorMap &c1, const CUtensorMap &c2,
+                const BwdArgs &a, cudaStream_t st) {
+  const int Lc = SIDE == 0 ? a.Lk : a.Lq;
+  const int NC = (Lc + 15) & ~15;
+  const size_t smem = 32768 + (size_t)NC * 256 + (SIDE == 1 ? 32768 : 16384) +
+                      (size_t)(SIDE == 0 ? NC + 768 : 9 * NC) * 4 + 64;
+  constexpr size_t SMEM_MAX = 32768 + 256 * 256 + 32768 + 9 * 256 * 4 + 64;
+  auto kern = attn_bwd_kernel<SIDE, GATED, DROP>;
+  static bool configured[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return SV_ERR_INVALID_ARG;
+  if (!configured[dev]) {
+    int rc = sv::cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
+    if (rc) return rc;
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    configured[dev] = true;
+  }
+  kern<<<a.B * a.H, 256, smem, st>>>(r1, r2, c1, c2, a);
   return sv::after_launch();
 }
-template <int NQCH>
-int launch_kv(const BwdArgs &a, cudaStream_t st) {
-  constexpr int NQP = NQCH * 32;
-  constexpr size_t smem = (size_t)2 * 128 * DH * 2 + (size_t)4 * NQP * DH * 2 + (size_t)2 * 128 * NQP * 2 + (size_t)NQP * 8 * 4 + 32;
-  auto kern = attention_bwd_kv_kernel<NQCH>;
-  int rc = sv::cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+
+template <bool GATED, bool DROP>
+int launch_both(const CUtensorMap &mq, const CUtensorMap &mk, const CUtensorMap &mv, const CUtensorMap &mo,
+                const BwdArgs &a, cudaStream_t st) {
+  int rc = launch_side<0, GATED, DROP>(mq, mo, mk, mv, a, st);
   if (rc) return rc;
-  kern<<<a.B * a.H, 128, smem, st>>>(a);
-  return sv::after_launch();
+  return launch_side<1, GATED, DROP>(mk, mv, mq, mo, a, st);
 }
 
 }  // namespace
@@ -439,38 +429,38 @@ extern "C" int sv_attention_bwd_dropout_bf16(const void *q, long long q_bs, int 
                                              int H, int Lq, int Lk, float scale, void *dq, void *dk, void *dv,
                                              float *d_spatial_w, float *dvec, float dropout_p, unsigned long long seed,
                                              void *stream) {
-  if (dropout_p < 0.f || dropout_p >= 1.f) return SV_ERR_INVALID_ARG;
-  if (B < 0 || H < 1 || Lq < 1 || Lk < 1 || Lq > 160 || Lk > 160) return SV_ERR_INVALID_ARG;
+  if (!(dropout_p >= 0.f) || dropout_p >= 1.f) return SV_ERR_INVALID_ARG;
+  if (B < 0 || H < 1 || Lq < 1 || Lk < 1 || Lq > 256 || Lk > 256) return SV_ERR_INVALID_ARG;
   if (B == 0) return SV_OK;
   if (!q || !k || !v || !o || !d_o || !lse || !dq || !dk || !dv || !dvec) return SV_ERR_INVALID_ARG;
   if ((q_rs % 8) || (k_rs % 8) || (v_rs % 8) || (q_bs % 8) || (k_bs % 8) || (v_bs % 8)) return SV_ERR_INVALID_ARG;
+  if ((reinterpret_cast<uintptr_t>(q) & 15) || (reinterpret_cast<uintptr_t>(k) & 15) ||
+      (reinterpret_cast<uintptr_t>(v) & 15) || (reinterpret_cast<uintptr_t>(o) & 15) ||
+      (reinterpret_cast<uintptr_t>(d_o) & 15) || (reinterpret_cast<uintptr_t>(dq) & 15) ||
+      (reinterpret_cast<uintptr_t>(dk) & 15) || (reinterpret_cast<uintptr_t>(dv) & 15))
+    return SV_ERR_INVALID_ARG;
   if (spatial_w && (!pairwise_locs || !d_spatial_w)) return SV_ERR_INVALID_ARG;
+  if (spatial_w && dropout_p > 0.f) return SV_ERR_INVALID_ARG;
   BwdArgs a;
-  a.q = (const __nv_bfloat16 *)q; a.k = (const __nv_bfloat16 *)k; a.v = (const __nv_bfloat16 *)v;
-  a.q_bs = q_bs; a.k_bs = k_bs; a.v_bs = v_bs; a.q_rs = q_rs; a.k_rs = k_rs; a.v_rs = v_rs;
   a.o = (const __nv_bfloat16 *)o; a.d_o = (const __nv_bfloat16 *)d_o;
   a.kpm = key_padding_mask; a.sw = spatial_w; a.locs = pairwise_locs; a.lse = lse;
   a.B = B; a.H = H; a.Lq = Lq; a.Lk = Lk; a.scale = scale;
   a.dq = (__nv_bfloat16 *)dq; a.dk = (__nv_bfloat16 *)dk; a.dv = (__nv_bfloat16 *)dv;
   a.dsw = d_spatial_w; a.dvec = dvec;
-  a.drop_thresh = dropout_p > 0.f ? (unsigned)((double)dropout_p * 4294967296.0) : 0u;
+  a.t16 = drop_threshold(dropout_p);
   a.inv_keep = 1.0f / (1.0f - dropout_p);
   a.seed = seed;
-  cudaStream_t st = (cudaStream_t)stream;
-  int rc;
-  switch ((Lk + 31) / 32) {
-    case 1: rc = launch_q<1>(a, st); break;
-    case 2: rc = launch_q<2>(a, st); break;
-    case 3: rc = launch_q<3>(a, st); break;
-    case 4: rc = launch_q<4>(a, st); break;
-    default: rc = launch_q<5>(a, st); break;
-  }
+  CUtensorMap mq, mk, mv, mo;
+  int rc = make_map(&mq, q, B, Lq, H, q_rs, q_bs);
   if (rc) return rc;
-  switch ((Lq + 31) / 32) {
-    case 1: return launch_kv<1>(a, st);
-    case 2: return launch_kv<2>(a, st);
-    case 3: return launch_kv<3>(a, st);
-    case 4: return launch_kv<4>(a, st);
-    default: return launch_kv<5>(a, st);
-  }
+  rc = make_map(&mk, k, B, Lk, H, k_rs, k_bs);
+  if (rc) return rc;
+  rc = make_map(&mv, v, B, Lk, H, v_rs, v_bs);
+  if (rc) return rc;
+  rc = make_map(&mo, d_o, B, Lq, H, H * DH, (long long)Lq * H * DH);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (spatial_w) return launch_both<true, false>(mq, mk, mv, mo, a, st);
+  if (a.t16) return launch_both<false, true>(mq, mk, mv, mo, a, st);
+  return launch_both<false, false>(mq, mk, mv, mo, a, st);
 }

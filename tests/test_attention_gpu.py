@@ -10,7 +10,7 @@ def rand(*shape, seed=0, scale=1.0):
     return torch.randn(*shape, device="cuda", generator=g) * scale
 
 
-@pytest.mark.parametrize("Lq,Lk", [(80, 80), (130, 130), (80, 50), (50, 80), (50, 50), (32, 32), (1, 7), (129, 160)])
+@pytest.mark.parametrize("Lq,Lk", [(80, 80), (130, 130), (80, 50), (50, 80), (50, 50), (32, 32), (1, 7), (129, 160), (300, 256), (17, 200)])
 def test_plain_attention(Lq, Lk):
     from sceneverse_b200 import native, ops
     B, H, E = 3, 12, 768
@@ -110,7 +110,7 @@ def test_fused_cross_entropy_matches_torch(dtype):
     assert abs(float(l2) - float(want)) < 1e-5 and torch.isfinite(og.grad).all()
 
 
-@pytest.mark.parametrize("Lq,Lk", [(80, 80), (130, 130), (50, 80), (80, 50), (33, 7)])
+@pytest.mark.parametrize("Lq,Lk", [(80, 80), (130, 130), (50, 80), (80, 50), (33, 7), (256, 200), (129, 65)])
 def test_plain_attention_backward_native(Lq, Lk):
     from sceneverse_b200 import ops
     B, H, E = 3, 12, 768
@@ -136,15 +136,28 @@ def test_plain_attention_backward_native(Lq, Lk):
         assert err < 3e-2, (name, err)
 
 
-def _fmix64_keep(seed, idx, p):
+def _dropout_keep(seed, B, H, Lq, Lk, p):
+    """numpy restatement of csrc/attn_common.cuh drop_row_key / drop_pair_hash / drop_keep."""
     import numpy as np
-    x = (idx + np.uint64(seed)).astype(np.uint64)
-    x ^= x >> np.uint64(33)
-    x *= np.uint64(0xff51afd7ed558ccd)
-    x ^= x >> np.uint64(33)
-    x *= np.uint64(0xc4ceb9fe1a85ec53)
-    x ^= x >> np.uint64(33)
-    return (x & np.uint64(0xffffffff)) >= np.uint64(int(p * 4294967296.0))
+    M64, M32 = np.uint64(0xFFFFFFFFFFFFFFFF), np.uint64(0xFFFFFFFF)
+    with np.errstate(over="ignore"):
+        rows = np.arange(B * H * Lq, dtype=np.uint64)
+        x = (np.uint64(seed) + rows * np.uint64(0x9E3779B97F4A7C15)) & M64
+        x ^= x >> np.uint64(33)
+        x = (x * np.uint64(0xff51afd7ed558ccd)) & M64
+        x ^= x >> np.uint64(33)
+        x = (x * np.uint64(0xc4ceb9fe1a85ec53)) & M64
+        x ^= x >> np.uint64(33)
+        rk = (x & M32)[:, None]                                   # (rows, 1)
+        j = np.arange(Lk, dtype=np.uint64)[None, :]
+        h = rk ^ (((j >> np.uint64(1)) * np.uint64(0x9E3779B1)) & M32)
+        h ^= h >> np.uint64(16)
+        h = (h * np.uint64(0x85EBCA6B)) & M32
+        h ^= h >> np.uint64(13)
+        h = (h * np.uint64(0xC2B2AE35)) & M32
+        h ^= h >> np.uint64(16)
+        u16 = (h >> ((j & np.uint64(1)) * np.uint64(16))) & np.uint64(0xFFFF)
+    return (u16 >= np.uint64(int(p * 65536.0 + 0.5))).reshape(B, H, Lq, Lk)
 
 
 @pytest.mark.parametrize("Lq,Lk", [(130, 130), (80, 50)])
@@ -158,9 +171,7 @@ def test_attention_dropout_forward_backward(Lq, Lk):
     go = rand(B, Lq, E, seed=4).bfloat16()
     out, lse = native.attention(q, k, v, H, return_lse=True, dropout_p=p, seed=seed)
     dq, dk, dv, _ = native.attention_backward(q, k, v, out, go, lse, H, dropout_p=p, seed=seed)
-    with np.errstate(over="ignore"):
-        idx = np.arange(B * H * Lq * Lk, dtype=np.uint64)
-        keep = torch.from_numpy(_fmix64_keep(seed, idx, p).reshape(B, H, Lq, Lk)).cuda()
+    keep = torch.from_numpy(_dropout_keep(seed, B, H, Lq, Lk, p)).cuda()
     assert abs(keep.float().mean().item() - (1 - p)) < 0.01
     qf, kf, vf = (t.float().requires_grad_(True) for t in (q, k, v))
     qh = qf.view(B, Lq, H, 64).transpose(1, 2); kh = kf.view(B, Lk, H, 64).transpose(1, 2); vh = vf.view(B, Lk, H, 64).transpose(1, 2)
