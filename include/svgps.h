@@ -90,6 +90,23 @@ int sv_attention_bwd_dropout_bf16(const void *q, long long q_bs, int q_rs, const
                                   void *dq, void *dk, void *dv, float *d_spatial_w, float *dvec, float dropout_p,
                                   unsigned long long seed, void *stream);
 
+/* Fused dropout + residual add + LayerNorm:  y = LayerNorm(residual + dropout(x)) * gamma + beta  (reference: the post-norm
+ * blocks of modules/layers/transformers.py:145-154,311-315; plain LayerNorm of modules/utils.py:18-25 with residual = NULL,
+ * dropout_p = 0).  x, residual, y, s: (R,D) contiguous, bf16 (io_bf16 = 1) or f32; D % 8 == 0, D <= 1024; gamma, beta (D)
+ * f32; s receives the pre-norm sum (required when residual != NULL or dropout_p > 0; the backward's input — with neither,
+ * pass x itself to the backward); mean, rstd (R) f32.  The dropout mask is the counter hash of csrc/attn_common.cuh keyed
+ * by (seed, row, column): nothing is stored, the backward regenerates it. */
+int sv_layer_norm_fwd(const void *x, const void *residual, int io_bf16, int R, int D, const float *gamma, const float *beta,
+                      float eps, float dropout_p, unsigned long long seed, void *y, void *s, float *mean, float *rstd,
+                      void *stream);
+/* Backward: g = dL/dy (R,D) same dtype; ds = dL/d(residual) (= dL/dx without dropout); dx = ds o mask / (1 - p) (required
+ * iff dropout_p > 0); dgamma, dbeta (D) f32; scratch: sv_layer_norm_scratch_floats(D) floats (per-CTA partial sums, reduced
+ * in a fixed order by a second small kernel). */
+int sv_layer_norm_bwd(const void *g, const void *s, int io_bf16, int R, int D, const float *gamma, const float *mean,
+                      const float *rstd, float dropout_p, unsigned long long seed, void *ds, void *dx, float *dgamma,
+                      float *dbeta, float *scratch, void *stream);
+int sv_layer_norm_scratch_floats(int D);
+
 /* calc_pairwise_locs, 'center' relation (reference: modules/utils.py:38-87): centers (B,O,*) f32 with row stride
  * row_stride (>= 3 floats; xyz first) -> out (B,O,O,5) f32 = [dist/max_dist, dz/dist, dist2d/dist, dy/dist2d, dx/dist2d];
  * dist_norm = 0 keeps the raw distance in slot 0.  eps sits inside the square roots (1e-10 in the reference). */
@@ -102,6 +119,11 @@ int sv_pairwise_locs_f32(const float *centers, int row_stride, int B, int O, flo
  * = softmax(row) - onehot(label) (zero rows for ignored labels).  The caller divides by the number of valid rows. */
 int sv_cross_entropy_fwd_bwd(const void *logits, long long row_stride, int is_bf16, const long long *labels, int R, int V,
                              long long ignore_index, float *loss_rows, void *grad_logits, void *stream);
+/* same, with gradient rows grad_row_stride (>= V) elements apart; columns [V, grad_row_stride) are written as zeros — the
+ * gradient of a vocabulary padded to 16-byte rows (BERT LM head, V = 30522 -> 30528) feeds the backward GEMMs directly */
+int sv_cross_entropy_fwd_bwd_strided(const void *logits, long long row_stride, int is_bf16, const long long *labels, int R,
+                                     int V, long long ignore_index, float *loss_rows, void *grad_logits,
+                                     long long grad_row_stride, void *stream);
 
 /* L2-normalise + all-gather fused over NVLink peer memory (reference: contra_loss.py:58-64,86-91 + dist_utils.py:131-149).
  * a, b: local (n,D) f32.  peer_bufs[world] / peer_signals[world]: DEVICE arrays of device pointers into a symmetric

@@ -69,6 +69,8 @@ _GPS_SIGS = {
     "sv_pairwise_locs_f32": [c_void_p, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p],
     "sv_cross_entropy_fwd_bwd": [c_void_p, ctypes.c_longlong, c_int, c_void_p, c_int, c_int, ctypes.c_longlong, c_void_p,
                                  c_void_p, c_void_p],
+    "sv_cross_entropy_fwd_bwd_strided": [c_void_p, ctypes.c_longlong, c_int, c_void_p, c_int, c_int, ctypes.c_longlong,
+                                         c_void_p, c_void_p, ctypes.c_longlong, c_void_p],
     "sv_normalize_allgather_f32": [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                    ctypes.c_uint, c_void_p],
     "sv_attention_fwd_lse_bf16": [c_void_p, ctypes.c_longlong, c_int, c_void_p, ctypes.c_longlong, c_int, c_void_p,
@@ -85,6 +87,11 @@ _GPS_SIGS = {
                                       ctypes.c_longlong, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_float, ctypes.c_ulonglong, c_void_p],
+    "sv_layer_norm_fwd": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_float, ctypes.c_ulonglong,
+                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "sv_layer_norm_bwd": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_float, ctypes.c_ulonglong,
+                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "sv_layer_norm_scratch_floats": [c_int],
     "sv_sa_mlp_param_bytes": [c_int],
     "sv_sa1_mlp_bf16": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
     "sv_sa2_mlp_bf16": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],

@@ -35,12 +35,14 @@ template <typename T>
 __global__ void __launch_bounds__(256) ce_fwd_bwd_kernel(const T *__restrict__ logits, long long row_stride,
                                                          const long long *__restrict__ labels, int V,
                                                          long long ignore_index, float *__restrict__ loss_rows,
-                                                         T *__restrict__ grad) {
+                                                         T *__restrict__ grad, long long grad_stride) {
   __shared__ float red[8];
   const long long r = blockIdx.x;
   const long long label = labels[r];
   const T *x = logits + r * row_stride;
-  T *g = grad ? grad + r * (long long)V : nullptr;
+  T *g = grad ? grad + r * grad_stride : nullptr;
+  if (g)  // padding columns of a padded-vocabulary gradient (grad_stride > V) are always zero
+    for (int j = V + threadIdx.x; j < grad_stride; j += 256) st(g, j, 0.f);
   if (label == ignore_index || label < 0 || label >= V) {
     if (threadIdx.x == 0) loss_rows[r] = 0.f;
     if (g)
@@ -66,15 +68,23 @@ __global__ void __launch_bounds__(256) ce_fwd_bwd_kernel(const T *__restrict__ l
 extern "C" int sv_cross_entropy_fwd_bwd(const void *logits, long long row_stride, int is_bf16, const long long *labels,
                                         int R, int V, long long ignore_index, float *loss_rows, void *grad_logits,
                                         void *stream) {
-  if (R < 0 || V < 1) return SV_ERR_INVALID_ARG;
+  return sv_cross_entropy_fwd_bwd_strided(logits, row_stride, is_bf16, labels, R, V, ignore_index, loss_rows, grad_logits,
+                                          V, stream);
+}
+
+extern "C" int sv_cross_entropy_fwd_bwd_strided(const void *logits, long long row_stride, int is_bf16,
+                                                const long long *labels, int R, int V, long long ignore_index,
+                                                float *loss_rows, void *grad_logits, long long grad_row_stride,
+                                                void *stream) {
+  if (R < 0 || V < 1 || grad_row_stride < V) return SV_ERR_INVALID_ARG;
   if (R == 0) return SV_OK;
   if (!logits || !labels || !loss_rows) return SV_ERR_INVALID_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   if (is_bf16)
     ce_fwd_bwd_kernel<__nv_bfloat16><<<R, 256, 0, st>>>((const __nv_bfloat16 *)logits, row_stride, labels, V,
-                                                        ignore_index, loss_rows, (__nv_bfloat16 *)grad_logits);
+                                                        ignore_index, loss_rows, (__nv_bfloat16 *)grad_logits, grad_row_stride);
   else
     ce_fwd_bwd_kernel<float><<<R, 256, 0, st>>>((const float *)logits, row_stride, labels, V, ignore_index, loss_rows,
-                                                (float *)grad_logits);
+                                                (float *)grad_logits, grad_row_stride);
   return sv::after_launch();
 }

@@ -9,6 +9,7 @@ import torch
 from torch import nn
 
 from .modules import grounding, heads, vision  # noqa: F401  (populate the registries)
+from . import ops
 from .modules.registry import LANGUAGE_REGISTRY, build_module
 
 
@@ -36,9 +37,29 @@ class BERTLanguageEncoder(nn.Module):
         self.bert_config = BertConfig(hidden_size=hidden_size, num_hidden_layers=num_hidden_layers,
                                       num_attention_heads=num_attention_heads, type_vocab_size=type_vocab_size)
         self.model = BertModel(self.bert_config)  # no network: random init instead of from_pretrained(weights)
+        _fuse_bert_layer_norms(self.model)
 
     def forward(self, txt_ids, txt_masks, **kwargs):
         return self.model(txt_ids, txt_masks).last_hidden_state
+
+
+def _bert_output_forward(self, hidden_states, input_tensor):
+    """BertSelfOutput / BertOutput tail LayerNorm(input + dropout(dense(h))) through the fused native kernel."""
+    h = ops.linear(hidden_states, self.dense.weight, self.dense.bias)
+    return self.LayerNorm(h, residual=input_tensor, dropout_p=self.dropout.p if self.training else 0.0)
+
+
+def _fuse_bert_layer_norms(bert):
+    """Same modules, parameters and state_dict keys as the HF model; only the forward of the LayerNorms (and of the two
+    residual tails of every block) is routed to ops.layer_norm."""
+    import types
+    from .modules.layers import LayerNorm
+    for mod in bert.modules():
+        if type(mod) is nn.LayerNorm:
+            mod.__class__ = LayerNorm
+    for layer in bert.encoder.layer:
+        for tail in (layer.attention.output, layer.output):
+            tail.forward = types.MethodType(_bert_output_forward, tail)
 
 
 def no_decay_param_group(parameters, lr):

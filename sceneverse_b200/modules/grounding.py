@@ -2,13 +2,13 @@
 import torch
 from torch import nn
 
-from .layers import (TransformerDecoderLayer, TransformerEncoderLayer, TransformerSpatialDecoderLayer,
+from .layers import (LayerNorm, TransformerDecoderLayer, TransformerEncoderLayer, TransformerSpatialDecoderLayer,
                      calc_pairwise_locs, init_weights_bert, layer_repeat)
 from .registry import GROUNDING_REGISTRY
 
 
 def _loc_layers(dim_loc, hidden_size):
-    return layer_repeat(nn.Sequential(nn.Linear(dim_loc, hidden_size), nn.LayerNorm(hidden_size)), 1)
+    return layer_repeat(nn.Sequential(nn.Linear(dim_loc, hidden_size), LayerNorm(hidden_size)), 1)
 
 
 @GROUNDING_REGISTRY.register()

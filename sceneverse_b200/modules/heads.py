@@ -3,7 +3,7 @@ import torch
 from torch import nn
 
 from .. import ops
-from .layers import get_mlp_head
+from .layers import LayerNorm, get_mlp_head
 from .registry import HEADS_REGISTRY
 
 
@@ -44,7 +44,7 @@ class _Transform(nn.Module):
 
     def __init__(self, width):
         super().__init__()
-        self.dense, self.LayerNorm = nn.Linear(width, width), nn.LayerNorm(width)
+        self.dense, self.LayerNorm = nn.Linear(width, width), LayerNorm(width)
 
 
 class BertLMPredictionHead(nn.Module):
@@ -61,7 +61,7 @@ class BertLMPredictionHead(nn.Module):
     def forward(self, hidden_states):
         t = self.transform
         h = t.LayerNorm(ops.linear(hidden_states, t.dense.weight, t.dense.bias, activation="gelu"))
-        return ops.linear(h, self.decoder.weight, self.bias)
+        return ops.padded_vocab_linear(h, self.decoder.weight, self.bias)
 
 
 def _lm_heads(owner, hidden_size, **vocabs):

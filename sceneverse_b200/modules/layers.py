@@ -22,9 +22,17 @@ def get_activation_fn(activation_type):
     return getattr(F, activation_type)
 
 
+class LayerNorm(nn.LayerNorm):
+    """nn.LayerNorm (same parameters / state_dict) whose forward is the fused native dropout + residual + LayerNorm:
+    norm(x, residual=r, dropout_p=p) == LayerNorm(r + dropout(x))."""
+
+    def forward(self, x, residual=None, dropout_p=0.0):
+        return ops.layer_norm(x, self.weight, self.bias, self.eps, residual=residual, dropout_p=dropout_p)
+
+
 def get_mlp_head(input_size, hidden_size, output_size, dropout=0):
     """modules/utils.py:18-25 (note LayerNorm eps=1e-12)."""
-    return nn.Sequential(nn.Linear(input_size, hidden_size), nn.ReLU(), nn.LayerNorm(hidden_size, eps=1e-12),
+    return nn.Sequential(nn.Linear(input_size, hidden_size), nn.ReLU(), LayerNorm(hidden_size, eps=1e-12),
                          nn.Dropout(dropout), nn.Linear(hidden_size, output_size))
 
 
@@ -121,8 +129,8 @@ class TransformerEncoderLayer(nn.Module):
         self.linear1 = nn.Linear(d_model, dim_feedforward)
         self.dropout = nn.Dropout(dropout)
         self.linear2 = nn.Linear(dim_feedforward, d_model)
-        self.norm1 = nn.LayerNorm(d_model)
-        self.norm2 = nn.LayerNorm(d_model)
+        self.norm1 = LayerNorm(d_model)
+        self.norm2 = LayerNorm(d_model)
         self.dropout1 = nn.Dropout(dropout)
         self.dropout2 = nn.Dropout(dropout)
         self.activation_name = activation
@@ -136,15 +144,15 @@ class TransformerEncoderLayer(nn.Module):
     def forward(self, tgt, tgt_mask=None, tgt_key_padding_mask=None):
         tgt2 = self.norm1(tgt) if self.prenorm else tgt
         tgt2, attn = self.self_attn(tgt2, tgt2, tgt2, attn_mask=tgt_mask, key_padding_mask=tgt_key_padding_mask)
-        tgt = tgt + self.dropout1(tgt2)
-        if not self.prenorm:
-            tgt = self.norm1(tgt)
         if self.prenorm:
-            tgt = self.norm2(tgt)
-        tgt = tgt + self.dropout2(self._ffn(tgt))
-        if not self.prenorm:
-            tgt = self.norm2(tgt)
+            tgt = self.norm2(tgt + self.dropout1(tgt2))
+            return tgt + self.dropout2(self._ffn(tgt)), attn
+        tgt = self.norm1(tgt2, residual=tgt, dropout_p=self._p(self.dropout1))
+        tgt = self.norm2(self._ffn(tgt), residual=tgt, dropout_p=self._p(self.dropout2))
         return tgt, attn
+
+    def _p(self, drop):
+        return drop.p if self.training else 0.0
 
 
 class TransformerSpatialEncoderLayer(TransformerEncoderLayer):
@@ -159,8 +167,8 @@ class TransformerSpatialEncoderLayer(TransformerEncoderLayer):
 
     def forward(self, tgt, tgt_pairwise_locs, tgt_mask=None, tgt_key_padding_mask=None):
         tgt2, attn = self.self_attn(tgt, tgt, tgt, tgt_pairwise_locs, key_padding_mask=tgt_key_padding_mask)
-        tgt = self.norm1(tgt + self.dropout1(tgt2))
-        tgt = self.norm2(tgt + self.dropout2(self._ffn(tgt)))
+        tgt = self.norm1(tgt2, residual=tgt, dropout_p=self._p(self.dropout1))
+        tgt = self.norm2(self._ffn(tgt), residual=tgt, dropout_p=self._p(self.dropout2))
         return tgt, attn
 
 
@@ -174,9 +182,9 @@ class TransformerDecoderLayer(nn.Module):
         self.linear1 = nn.Linear(d_model, dim_feedforward)
         self.dropout = nn.Dropout(dropout)
         self.linear2 = nn.Linear(dim_feedforward, d_model)
-        self.norm1 = nn.LayerNorm(d_model)
-        self.norm2 = nn.LayerNorm(d_model)
-        self.norm3 = nn.LayerNorm(d_model)
+        self.norm1 = LayerNorm(d_model)
+        self.norm2 = LayerNorm(d_model)
+        self.norm3 = LayerNorm(d_model)
         self.dropout1 = nn.Dropout(dropout)
         self.dropout2 = nn.Dropout(dropout)
         self.dropout3 = nn.Dropout(dropout)

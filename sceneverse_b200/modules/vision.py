@@ -6,7 +6,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from .layers import TransformerSpatialEncoderLayer, calc_pairwise_locs, init_weights_bert, layer_repeat
+from .layers import LayerNorm, TransformerSpatialEncoderLayer, calc_pairwise_locs, init_weights_bert, layer_repeat
 from .pointnet import GPS_SPEC, PointNetPP
 from .registry import VISION_REGISTRY
 
@@ -31,7 +31,7 @@ class PointOpenVocabEncoder(nn.Module):
         if freeze:  # only what exists at this point is frozen, as in the reference (:53-56)
             for p in self.parameters():
                 p.requires_grad = False
-        self.sem_cls_embed_layer = nn.Sequential(nn.Linear(hidden_size, hidden_size), nn.LayerNorm(hidden_size),
+        self.sem_cls_embed_layer = nn.Sequential(nn.Linear(hidden_size, hidden_size), LayerNorm(hidden_size),
                                                  nn.Dropout(0.1))
         self.use_matmul_label = use_matmul_label
         self.sem_mask_embeddings = nn.Embedding(1, 768)
@@ -40,7 +40,7 @@ class PointOpenVocabEncoder(nn.Module):
                                                    dropout=0.1, activation='gelu', spatial_dim=spatial_dim,
                                                    spatial_multihead=True, spatial_attn_fusion='cond')
             self.spatial_encoder = layer_repeat(layer, num_layers)
-            self.loc_layers = layer_repeat(nn.Sequential(nn.Linear(dim_loc, hidden_size), nn.LayerNorm(hidden_size)), 1)
+            self.loc_layers = layer_repeat(nn.Sequential(nn.Linear(dim_loc, hidden_size), LayerNorm(hidden_size)), 1)
             self.pairwise_rel_type = pairwise_rel_type
             self.spatial_dim = spatial_dim
         self.apply(init_weights_bert)

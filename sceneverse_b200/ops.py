@@ -12,7 +12,8 @@ NATIVE = {"linear": False,              # plain GEMM -> cuBLAS (library GEMM); f
           "attention": True,            # nn.MultiheadAttention core incl. attention dropout: native tcgen05 forward + backward
           "spatial_attention": True,    # MultiHeadAttentionSpatial core: native tcgen05 forward and backward
           "calc_pairwise_locs": True,
-          "cross_entropy": True}        # masked-LM / grounding CE: fused native forward+gradient
+          "cross_entropy": True,        # masked-LM / grounding CE: fused native forward+gradient
+          "layer_norm": True}           # dropout + residual add + LayerNorm: one native pass per direction
 
 
 _dropout_calls = [0]
@@ -175,22 +176,25 @@ def _spatial_attention_torch(q, k, v, spatial_weights, pairwise_locs, n_head, sp
 
 
 class _CrossEntropyFn(torch.autograd.Function):
-    """mean cross-entropy over the rows whose label != ignore_index; forward and gradient come from ONE native launch."""
+    """mean cross-entropy over the rows whose label != ignore_index; forward and gradient come from ONE native launch.
+    n_classes < logits.shape[1]: the trailing columns are padding (padded-vocabulary logits): ignored by the loss, zero in
+    the gradient, which keeps the padded row stride so the backward GEMMs stay 16-byte aligned."""
 
     @staticmethod
-    def forward(ctx, logits2d, labels, ignore_index):
+    def forward(ctx, logits2d, labels, ignore_index, n_classes):
         from . import _lib
-        R, V = logits2d.shape
+        R, W = logits2d.shape
+        V = n_classes if n_classes else W
         loss_rows = torch.empty(R, dtype=torch.float32, device=logits2d.device)
         need_grad = logits2d.requires_grad
-        grad = torch.empty((R, V), dtype=logits2d.dtype, device=logits2d.device) if need_grad else None
+        grad = torch.empty((R, W), dtype=logits2d.dtype, device=logits2d.device) if need_grad else None
         lib = _lib.gps()
         with torch.cuda.device(logits2d.device):
-            st = lib.sv_cross_entropy_fwd_bwd(logits2d.data_ptr(), logits2d.stride(0), 1 if logits2d.dtype == torch.bfloat16 else 0,
-                                              labels.data_ptr(), R, V, int(ignore_index), loss_rows.data_ptr(),
-                                              grad.data_ptr() if grad is not None else None,
-                                              torch.cuda.current_stream(logits2d.device).cuda_stream)
-        _lib.check(lib, st, "sv_cross_entropy_fwd_bwd")
+            st = lib.sv_cross_entropy_fwd_bwd_strided(
+                logits2d.data_ptr(), logits2d.stride(0), 1 if logits2d.dtype == torch.bfloat16 else 0, labels.data_ptr(), R,
+                V, int(ignore_index), loss_rows.data_ptr(), grad.data_ptr() if grad is not None else None, W,
+                torch.cuda.current_stream(logits2d.device).cuda_stream)
+        _lib.check(lib, st, "sv_cross_entropy_fwd_bwd_strided")
         count = (labels != ignore_index).sum().clamp(min=1).float()
         ctx.save_for_backward(grad, count)
         return loss_rows.sum() / count
@@ -198,15 +202,141 @@ class _CrossEntropyFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gout):
         grad, count = ctx.saved_tensors
-        return grad.mul_((gout / count).to(grad.dtype)), None, None
+        return grad.mul_((gout / count).to(grad.dtype)), None, None, None
+
+
+class _PaddedVocabLinearFn(torch.autograd.Function):
+    """logits_p = h @ Wp^T + bp with the class dimension zero-padded to a multiple of 64, so that every row of the logits
+    and of their gradient is 16-byte aligned: the forward runs on the native tcgen05 GEMM (bias fused), the two backward
+    GEMMs on aligned library kernels (an odd class count such as BERT's 30522 otherwise drops cuBLAS to a 4x slower
+    legacy kernel).  Reference: modules/heads/pretrain_head.py:22-32 (decoder + bias)."""
+
+    @staticmethod
+    def forward(ctx, h2, weight, bias):
+        from . import native
+        V, K = weight.shape
+        Vp = (V + 63) // 64 * 64
+        wp = torch.empty((Vp, K), dtype=torch.bfloat16, device=h2.device)
+        wp[:V].copy_(weight)
+        wp[V:].zero_()
+        bp = torch.zeros(Vp, dtype=torch.float32, device=h2.device)
+        bp[:V].copy_(bias)
+        ctx.save_for_backward(h2, wp)
+        ctx.V = V
+        return native.gemm(h2, wp, bias=bp)
+
+    @staticmethod
+    def backward(ctx, gp):
+        h2, wp = ctx.saved_tensors
+        V = ctx.V
+        gp = gp.contiguous()
+        dh = gp @ wp
+        dw = (gp.t() @ h2)[:V].float()
+        db = gp.sum(0, dtype=torch.float32)[:V]
+        return dh, dw, db
+
+
+def padded_vocab_linear(h, weight, bias):
+    """(..., K) -> (..., V) logits of a wide classifier.  CUDA bf16: computed as padded logits (see _PaddedVocabLinearFn);
+    the returned tensor is the (..., :V) view and carries the padded parent as `_sv_padded`, which ops.cross_entropy uses
+    to produce the padded gradient directly.  Otherwise: ops.linear."""
+    V, K = weight.shape
+    if h.is_cuda and (h.dtype == torch.bfloat16 or _autocast_on()) and K % 8 == 0 and V % 64 != 0 and bias is not None:
+        h2 = h.reshape(-1, K).to(torch.bfloat16).contiguous()
+        lp = _PaddedVocabLinearFn.apply(h2, weight, bias).view(*h.shape[:-1], -1)
+        out = lp[..., :V]
+        out._sv_padded = lp
+        return out
+    return linear(h, weight, bias)
+
+
+class _LayerNormFn(torch.autograd.Function):
+    """y = LayerNorm(residual + dropout(x)) in one native pass; the backward regenerates the dropout mask and produces
+    d(x), d(residual), d(gamma), d(beta) (gamma / beta partial sums reduced in a fixed order)."""
+
+    @staticmethod
+    def forward(ctx, x, residual, gamma, beta, eps, p, seed):
+        from . import _lib
+        D = x.shape[-1]
+        x2 = x.reshape(-1, D)
+        R = x2.shape[0]
+        r2 = residual.reshape(-1, D) if residual is not None else None
+        need_s = r2 is not None or p > 0.0
+        y = torch.empty_like(x2)
+        s = torch.empty_like(x2) if need_s else None
+        stats = torch.empty((2, R), dtype=torch.float32, device=x.device)
+        lib = _lib.gps()
+        with torch.cuda.device(x.device):
+            st = lib.sv_layer_norm_fwd(x2.data_ptr(), r2.data_ptr() if r2 is not None else None,
+                                       1 if x.dtype == torch.bfloat16 else 0, R, D, gamma.data_ptr(), beta.data_ptr(),
+                                       float(eps), float(p), int(seed), y.data_ptr(), s.data_ptr() if need_s else None,
+                                       stats[0].data_ptr(), stats[1].data_ptr(),
+                                       torch.cuda.current_stream(x.device).cuda_stream)
+        _lib.check(lib, st, "sv_layer_norm_fwd")
+        ctx.save_for_backward(s if need_s else x2, gamma, stats)
+        ctx.meta = (float(p), int(seed), residual is not None, x.shape)
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import _lib
+        s, gamma, stats = ctx.saved_tensors
+        p, seed, has_res, shape = ctx.meta
+        R, D = s.shape
+        g2 = g.reshape(R, D).to(s.dtype).contiguous()
+        ds = torch.empty_like(s)
+        dx = torch.empty_like(s) if p > 0.0 else None
+        dgb = torch.empty((2, D), dtype=torch.float32, device=s.device)
+        lib = _lib.gps()
+        scratch = torch.empty(lib.sv_layer_norm_scratch_floats(D), dtype=torch.float32, device=s.device)
+        with torch.cuda.device(s.device):
+            st = lib.sv_layer_norm_bwd(g2.data_ptr(), s.data_ptr(), 1 if s.dtype == torch.bfloat16 else 0, R, D,
+                                       gamma.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(), p, seed, ds.data_ptr(),
+                                       dx.data_ptr() if dx is not None else None, dgb[0].data_ptr(), dgb[1].data_ptr(),
+                                       scratch.data_ptr(), torch.cuda.current_stream(s.device).cuda_stream)
+        _lib.check(lib, st, "sv_layer_norm_bwd")
+        d_x = (dx if dx is not None else ds).view(shape)
+        return d_x, (ds.view(shape) if has_res else None), dgb[0], dgb[1], None, None, None
+
+
+def _autocast_on():
+    try:
+        return torch.is_autocast_enabled("cuda")
+    except TypeError:
+        return torch.is_autocast_enabled()
+
+
+def layer_norm(x, weight, bias, eps=1e-5, residual=None, dropout_p=0.0):
+    """LayerNorm(residual + dropout(x)) * weight + bias over the last dimension (post-norm block tail of
+    transformers.py:145-154,311-315; plain LayerNorm with residual=None, dropout_p=0).  The caller passes dropout_p = 0
+    outside training.  CUDA: one native kernel, I/O in bf16 under autocast / for bf16 inputs (statistics in fp32), else
+    fp32; CPU: the torch formulation."""
+    D = x.shape[-1]
+    if x.is_cuda and D % 8 == 0 and 8 <= D <= 1024 and weight is not None and bias is not None and x.numel() > 0 and \
+            x.dtype in (torch.bfloat16, torch.float32, torch.float16):
+        low = x.dtype != torch.float32 or (residual is not None and residual.dtype != torch.float32) or _autocast_on()
+        dt = torch.bfloat16 if low else torch.float32
+        x_ = x.to(dt).contiguous()
+        r_ = None
+        if residual is not None:
+            r_ = residual.to(dt).expand_as(x_).contiguous()
+        return _LayerNormFn.apply(x_, r_, weight.float().contiguous(), bias.float().contiguous(), eps, float(dropout_p),
+                                  _next_dropout_seed() if dropout_p > 0.0 else 0)
+    s = x if dropout_p == 0.0 else F.dropout(x, dropout_p, True)
+    if residual is not None:
+        s = residual + s
+    return F.layer_norm(s, (D,), weight, bias, eps)
 
 
 def cross_entropy(logits, labels, ignore_index=-100):
     """F.cross_entropy(logits.permute(0, 2, 1) / logits, labels, ignore_index=...) with the class dimension LAST in
     `logits` ((..., V) with (...) matching labels).  CUDA bf16/f32 -> fused native kernel; otherwise torch."""
     V = logits.shape[-1]
+    padded = getattr(logits, "_sv_padded", None)
+    if padded is not None and padded.is_cuda and padded.shape[:-1] == logits.shape[:-1] and padded.is_contiguous():
+        return _CrossEntropyFn.apply(padded.view(-1, padded.shape[-1]), labels.reshape(-1).contiguous(), ignore_index, V)
     if logits.is_cuda and logits.dtype in (torch.bfloat16, torch.float32) and logits.stride(-1) == 1:
         l2 = logits.reshape(-1, V)
         if l2.stride(1) == 1:
-            return _CrossEntropyFn.apply(l2, labels.reshape(-1).contiguous(), ignore_index)
+            return _CrossEntropyFn.apply(l2, labels.reshape(-1).contiguous(), ignore_index, 0)
     return F.cross_entropy(logits.reshape(-1, V).float(), labels.reshape(-1), ignore_index=ignore_index)

@@ -182,3 +182,90 @@ def test_attention_dropout_forward_backward(Lq, Lk):
     for g, w, name in zip((dq, dk, dv), (qf.grad, kf.grad, vf.grad), "qkv"):
         err = (g.float() - w).abs().max().item() / (w.abs().max().item() + 1e-9)
         assert err < 3e-2, (name, err)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("R,D", [(4000, 768), (37, 384), (5, 1024), (260, 8), (1, 256)])
+def test_layer_norm_native_matches_torch(dtype, R, D):
+    """Fused residual + LayerNorm (no dropout): forward and all four gradients against F.layer_norm in fp32."""
+    from sceneverse_b200 import ops
+    import torch.nn.functional as F
+    x = rand(R, D, seed=1).to(dtype).requires_grad_(True)
+    r = rand(R, D, seed=2).to(dtype).requires_grad_(True)
+    w = (1.0 + 0.1 * rand(D, seed=3)).requires_grad_(True)
+    b = (0.1 * rand(D, seed=4)).requires_grad_(True)
+    go = rand(R, D, seed=5).to(dtype)
+    for use_res in (True, False):
+        for t in (x, r, w, b):
+            t.grad = None
+        y = ops.layer_norm(x, w, b, 1e-5, residual=r if use_res else None)
+        assert y.dtype == dtype and isinstance(y.grad_fn, ops._LayerNormFn._backward_cls)
+        y.backward(go)
+        got = [y.detach().float()] + [t.grad.float().clone() for t in ((x, r, w, b) if use_res else (x, w, b))]
+        xf, rf, wf, bf = (t.detach().float().requires_grad_(True) for t in (x, r, w, b))
+        s = (xf + rf) if use_res else xf
+        if dtype == torch.bfloat16:
+            s = s + (s.detach().bfloat16().float() - s.detach())   # the kernel normalises the bf16-rounded sum
+        yr = F.layer_norm(s, (D,), wf, bf, 1e-5)
+        yr.backward(go.float())
+        want = [yr.detach()] + [t.grad for t in ((xf, rf, wf, bf) if use_res else (xf, wf, bf))]
+        tol = 2e-2 if dtype == torch.bfloat16 else 2e-5
+        for i, (g, wv) in enumerate(zip(got, want)):
+            err = (g - wv).abs().max().item() / (wv.abs().max().item() + 1e-9)
+            assert err < tol, (use_res, i, err)
+
+
+def test_layer_norm_dropout_mask_and_backward():
+    """Dropout inside the fused LayerNorm: the mask is the documented counter hash, so torch can be fed the same mask."""
+    from sceneverse_b200 import ops
+    import torch.nn.functional as F
+    R, D, p, seed = 300, 768, 0.1, 987654321
+    x = rand(R, D, seed=1).bfloat16().requires_grad_(True)
+    r = rand(R, D, seed=2).bfloat16().requires_grad_(True)
+    w = (1.0 + 0.1 * rand(D, seed=3)).requires_grad_(True)
+    b = (0.1 * rand(D, seed=4)).requires_grad_(True)
+    go = rand(R, D, seed=5).bfloat16()
+    y = ops._LayerNormFn.apply(x, r, w, b, 1e-5, p, seed)
+    y.backward(go)
+    keep = torch.from_numpy(_dropout_keep(seed, 1, 1, R, D, p)).cuda().view(R, D)
+    assert abs(keep.float().mean().item() - (1 - p)) < 0.01
+    xf, rf, wf, bf = (t.detach().float().requires_grad_(True) for t in (x, r, w, b))
+    s = rf + xf * keep / (1 - p)
+    s = s + (s.detach().bfloat16().float() - s.detach())
+    yr = F.layer_norm(s, (D,), wf, bf, 1e-5)
+    yr.backward(go.float())
+    for g, wv, name in zip((y, x.grad, r.grad, w.grad, b.grad), (yr, xf.grad, rf.grad, wf.grad, bf.grad), "yxrwb"):
+        err = (g.detach().float() - wv.detach()).abs().max().item() / (wv.abs().max().item() + 1e-9)
+        assert err < 2e-2, (name, err)
+    assert ((x.grad == 0) == ~keep).float().mean().item() > 0.999   # dropped positions get exactly zero gradient
+
+
+def test_padded_vocab_head_and_cross_entropy():
+    """LM-head decoder on the native GEMM with the vocabulary padded to 16-byte rows + CE on the padded logits:
+    loss and the gradients of the hidden states, decoder weight and bias against F.linear + F.cross_entropy (fp32)."""
+    from sceneverse_b200 import ops
+    import torch.nn.functional as F
+    R, K, V = 384, 768, 3001                      # odd class count, like BERT's 30522
+    h = rand(R, K, seed=1).bfloat16().requires_grad_(True)
+    W = (rand(V, K, seed=2) * 0.05).requires_grad_(True)
+    b = (rand(V, seed=3) * 0.1).requires_grad_(True)
+    labels = torch.randint(0, V, (R,), device="cuda")
+    labels[torch.rand(R, device="cuda") < 0.7] = -1
+    logits = ops.padded_vocab_linear(h, W, b)
+    assert logits.shape == (R, V) and logits._sv_padded.shape == (R, 3008)
+    assert float(logits._sv_padded[:, V:].abs().max()) == 0.0
+    loss = ops.cross_entropy(logits, labels, ignore_index=-1)
+    loss.backward()
+    hf, Wf, bf = (t.detach().float().requires_grad_(True) for t in (h, W, b))
+    ref_logits = F.linear(hf, Wf.bfloat16().float(), bf)
+    ref = F.cross_entropy(ref_logits, labels, ignore_index=-1)
+    ref.backward()
+    assert (logits.float() - ref_logits).abs().max().item() < 2e-2 * ref_logits.abs().max().item()
+    assert abs(float(loss) - float(ref)) < 5e-3 * max(1.0, abs(float(ref)))
+    for g, w, name in zip((h.grad, W.grad, b.grad), (hf.grad, Wf.grad, bf.grad), "hWb"):
+        assert g.dtype == (torch.bfloat16 if name == "h" else torch.float32)
+        err = (g.float() - w).abs().max().item() / (w.abs().max().item() + 1e-12)
+        assert err < 3e-2, (name, err)
+    # the plain slice view still works for consumers that do not know about the padding
+    loss2 = F.cross_entropy(ops.padded_vocab_linear(h.detach(), W.detach(), b.detach()).float(), labels, ignore_index=-1)
+    assert abs(float(loss2) - float(ref)) < 5e-3 * max(1.0, abs(float(ref)))
