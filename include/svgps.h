@@ -50,7 +50,7 @@ int sv_gemm_bf16(const void *A, int lda, const void *B, int ldb, int M, int N, i
  * [64h, 64h+64).  key_padding_mask (B,Lk) bytes, 1 = ignore (may be NULL).  spatial_w (B,Lq,spatial_heads*6) f32 =
  * [bias, w1..w5] per head and pairwise_locs (B,Lq,Lk,5) f32 enable the MultiHeadAttentionSpatial 'cond' gate
  * log(clamp(sigmoid(w . loc + b), 1e-6)) (reference: modules/layers/transformers.py:206-232); NULL = plain attention
- * (nn.MultiheadAttention core).  Lk <= 256.  out (B,Lq,H*64) bf16. */
+ * (nn.MultiheadAttention core).  Lk <= 384.  out (B,Lq,H*64) bf16. */
 int sv_attention_fwd_bf16(const void *q, long long q_bs, int q_rs, const void *k, long long k_bs, int k_rs,
                           const void *v, long long v_bs, int v_rs, void *out, long long o_bs, int o_rs,
                           const unsigned char *key_padding_mask, const float *spatial_w, int spatial_heads,
@@ -66,7 +66,7 @@ int sv_attention_fwd_lse_bf16(const void *q, long long q_bs, int q_rs, const voi
 /* Backward of the fused attention (one tcgen05 kernel template launched twice: dQ + gate-weight gradients with tile rows
  * == queries, dK/dV with tile rows == keys; both recompute P from Q, K, the gate and lse).  q/k/v as in the forward; o, d_o (B,Lq,H*64) bf16
  * contiguous; dq (B,Lq,H*64), dk, dv (B,Lk,H*64) bf16 contiguous; d_spatial_w (B,Lq,H*6) f32 (NULL without gate; gate
- * requires spatial_heads == H); dvec (B,H,Lq) f32 scratch.  Lq, Lk <= 256. */
+ * requires spatial_heads == H); dvec (B,H,Lq) f32 scratch.  Lq, Lk <= 384. */
 int sv_attention_bwd_bf16(const void *q, long long q_bs, int q_rs, const void *k, long long k_bs, int k_rs,
                           const void *v, long long v_bs, int v_rs, const void *o, const void *d_o,
                           const unsigned char *key_padding_mask, const float *spatial_w, const float *pairwise_locs,

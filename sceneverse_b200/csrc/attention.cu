@@ -1,4 +1,4 @@
-// Fused attention forward on tcgen05 for the GPS shapes (<= 256 keys, head dim 64):
+// Fused attention forward on tcgen05 for the GPS shapes (<= 384 keys, head dim 64):
 //   O = dropout(softmax( Q K^T / sqrt(64) + spatial_log_bias + key_padding_mask )) V          per (scene, head)
 // Replaces the attention core of
 //   * MultiHeadAttentionSpatial, 'cond' fusion (modules/layers/transformers.py:188-237): the per-(head, query)
@@ -49,8 +49,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
   uint8_t *sK = sQ + 16384;                  // [NK][64]  sw128
   uint8_t *sV = sK + NK * 128;               // [NK][64]  sw128 (read MN-major)
   uint8_t *sP = sV + NK * 128;               // [NK/8][128][8] K-major, no swizzle
-  float *kb = reinterpret_cast<float *>(sP + NK * 256);  // [256] additive key bias: 0 or -inf
-  float *xmax = kb + 256;                    // [2][128] per-warpgroup row maxima
+  float *kb = reinterpret_cast<float *>(sP + NK * 256);  // [384] additive key bias: 0 or -inf
+  float *xmax = kb + 384;                    // [2][128] per-warpgroup row maxima
   float *xsum = xmax + 256;                  // [2][128] per-warpgroup row sums
   uint64_t *bars = reinterpret_cast<uint64_t *>(xsum + 256);  // 0: K/V landed, 1: Q tile landed, 2: MMA done
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3);
@@ -77,10 +77,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
     tma_rows(sQ, &mq, h, 0, 8, a.Lq, b, &bars[1]);
   }
   if (warp == 1) tmem_alloc_n(tmem_slot, a.tmem_cols);
-  {
-    const int j = tid;  // 256 threads cover the 256 bias slots
+  for (int j = tid; j < 384; j += 256)
     kb[j] = (j < a.Lk && !(a.kpm != nullptr && a.kpm[(size_t)b * a.Lk + j])) ? 0.f : -INFINITY;
-  }
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -102,10 +100,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
       mbar_wait(&bars[1], ph_q);
       fence_after_sync();
       const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK);
-      const uint32_t idesc = idesc_kk(NK);
+      for (int n0 = 0; n0 < NK; n0 += 256) {  // one MMA covers at most 256 keys
+        const uint32_t idesc = idesc_kk(min(256, NK - n0));
 #pragma unroll
-      for (int ks = 0; ks < DH / 16; ++ks)
-        mma_bf16(tmem, make_desc_sw128(aQ + ks * 32), make_desc_sw128(aK + ks * 32), idesc, ks > 0);
+        for (int ks = 0; ks < DH / 16; ++ks)
+          mma_bf16(tmem + n0, make_desc_sw128(aQ + ks * 32), make_desc_sw128(aK + n0 * 128 + ks * 32), idesc, ks > 0);
+      }
       mma_commit(&bars[2]);
     }
     ph_q ^= 1u;
@@ -274,8 +274,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
 template <bool GATED, bool DROP>
 int launch_fwd(const CUtensorMap &mq, const CUtensorMap &mk, const CUtensorMap &mv, const FwdArgs &a, cudaStream_t st) {
   const int NK = (a.Lk + 15) & ~15;
-  const size_t smem = 16384 + (size_t)NK * 128 * 2 + (size_t)NK * 256 + 3 * 1024 + 64;
-  constexpr size_t SMEM_MAX = 16384 + 256 * 128 * 2 + 256 * 256 + 3 * 1024 + 64;
+  const size_t smem = 16384 + (size_t)NK * 128 * 2 + (size_t)NK * 256 + (384 + 512) * 4 + 64;
+  constexpr size_t SMEM_MAX = 16384 + 384 * 128 * 2 + 384 * 256 + (384 + 512) * 4 + 64;
   auto kern = attn_fwd_kernel<GATED, DROP>;
   static bool configured[64] = {false};
   int dev = 0;
@@ -319,7 +319,7 @@ extern "C" int sv_attention_fwd_dropout_bf16(const void *q, long long q_bs, int 
                                              float scale, float *lse, float dropout_p, unsigned long long seed,
                                              void *stream) {
   if (!(dropout_p >= 0.f) || dropout_p >= 1.f) return SV_ERR_INVALID_ARG;
-  if (B < 0 || H < 1 || Lq < 0 || Lk < 1 || Lk > 256) return SV_ERR_INVALID_ARG;
+  if (B < 0 || H < 1 || Lq < 0 || Lk < 1 || Lk > 384) return SV_ERR_INVALID_ARG;
   if (B == 0 || Lq == 0) return SV_OK;
   if (!q || !k || !v || !out) return SV_ERR_INVALID_ARG;
   if ((q_rs % 8) || (k_rs % 8) || (v_rs % 8) || (o_rs % 8) || (q_bs % 8) || (k_bs % 8) || (v_bs % 8) || (o_bs % 8))

@@ -385,7 +385,7 @@ int launch_side(const CUtensorMap &r1, const CUtensorMap &r2, const CUtensorMap 
   const int NC = (Lc + 15) & ~15;
   const size_t smem = 32768 + (size_t)NC * 256 + (SIDE == 1 ? 32768 : 16384) +
                       (size_t)(SIDE == 0 ? NC + 768 : 9 * NC) * 4 + 64;
-  constexpr size_t SMEM_MAX = 32768 + 256 * 256 + 32768 + 9 * 256 * 4 + 64;
+  constexpr size_t SMEM_MAX = 32768 + 384 * 256 + 32768 + 9 * 384 * 4 + 64;
   auto kern = attn_bwd_kernel<SIDE, GATED, DROP>;
   static bool configured[64] = {false};
   int dev = 0;
@@ -430,7 +430,7 @@ extern "C" int sv_attention_bwd_dropout_bf16(const void *q, long long q_bs, int 
                                              float *d_spatial_w, float *dvec, float dropout_p, unsigned long long seed,
                                              void *stream) {
   if (!(dropout_p >= 0.f) || dropout_p >= 1.f) return SV_ERR_INVALID_ARG;
-  if (B < 0 || H < 1 || Lq < 1 || Lk < 1 || Lq > 256 || Lk > 256) return SV_ERR_INVALID_ARG;
+  if (B < 0 || H < 1 || Lq < 1 || Lk < 1 || Lq > 384 || Lk > 384) return SV_ERR_INVALID_ARG;
   if (B == 0) return SV_OK;
   if (!q || !k || !v || !o || !d_o || !lse || !dq || !dk || !dv || !dvec) return SV_ERR_INVALID_ARG;
   if ((q_rs % 8) || (k_rs % 8) || (v_rs % 8) || (q_bs % 8) || (k_bs % 8) || (v_bs % 8)) return SV_ERR_INVALID_ARG;

@@ -6,8 +6,9 @@
 // gamma/beta-gradient reduction in the backward; here it is one HBM-bound pass per direction:
 //   forward : one warp per row, the row lives in registers (two-pass mean / variance), the dropout mask is the counter
 //             hash of csrc/attn_common.cuh (nothing stored), the pre-norm sum s is written once for the backward;
-//   backward: one warp per row for ds (and dx = ds o mask / (1 - p)); gamma / beta gradients accumulate in registers over a
-//             grid-stride loop, are combined per CTA in shared memory and finished by a small deterministic second kernel.
+//   backward: one warp per row for ds (and dx = ds o mask / (1 - p)); the gamma / beta gradients come from a second,
+//             column-owning pass over g and s (L2-resident right after the first) whose per-CTA partial sums are
+//             finished by a small fixed-order reduction — deterministic, no atomics.
 // Algorithmic bytes per row (bf16 I/O, D columns): forward 2D (x) + 2D (residual) + 2D (s) + 2D (y) = 8D;
 // backward 2D (g) + 2D (s) + 2D (ds) [+ 2D (dx)].
 #include <cuda_bf16.h>
@@ -162,19 +163,11 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const LnArgs a) {
   }
 }
 
+// backward, part 1: ds (and dx) — one warp per row, nothing carried across rows (gamma is re-read from L1 per row)
 template <typename T, int MAXCH, bool DROP>
-__global__ void __launch_bounds__(256) ln_bwd_kernel(const LnArgs a) {
-  extern __shared__ float acc[];  // [2][D]
+__global__ void __launch_bounds__(256) ln_bwd_dx_kernel(const LnArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nch = a.D >> 3;
-  float gam[MAXCH][8], pg[MAXCH][8], pb[MAXCH][8];
-#pragma unroll
-  for (int ch = 0; ch < MAXCH; ++ch) {
-    const int c = lane + 32 * ch;
-    if (c < nch) Chunk<float>::load(a.gamma, c, gam[ch]);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) pg[ch][i] = pb[ch][i] = 0.f;
-  }
   const float invD = 1.0f / (float)a.D;
   for (int row = blockIdx.x * 8 + warp; row < a.R; row += gridDim.x * 8) {
     const size_t base8 = (size_t)row * nch;
@@ -185,17 +178,16 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnArgs a) {
     for (int ch = 0; ch < MAXCH; ++ch) {
       const int c = lane + 32 * ch;
       if (c < nch) {
-        float g[8], s[8];
+        float g[8], s[8], gam[8];
         Chunk<T>::load(a.g, base8 + c, g);
         Chunk<T>::load(a.s_in, base8 + c, s);
+        Chunk<float>::load(a.gamma, c, gam);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           xh[ch][i] = (s[i] - mean) * rstd;
-          gy[ch][i] = g[i] * gam[ch][i];
+          gy[ch][i] = g[i] * gam[i];
           s1 += gy[ch][i];
           s2 = fmaf(gy[ch][i], xh[ch][i], s2);
-          pg[ch][i] = fmaf(g[i], xh[ch][i], pg[ch][i]);
-          pb[ch][i] += g[i];
         }
       }
     }
@@ -221,39 +213,64 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnArgs a) {
       }
     }
   }
-  // combine the 8 warps of the CTA, one warp at a time (deterministic order), then write this CTA's partial
-  for (int w = 0; w < 8; ++w) {
-    if (warp == w) {
-#pragma unroll
-      for (int ch = 0; ch < MAXCH; ++ch) {
-        const int c = lane + 32 * ch;
-        if (c < nch) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int d = c * 8 + i;
-            if (w == 0) {
-              acc[d] = pg[ch][i];
-              acc[a.D + d] = pb[ch][i];
-            } else {
-              acc[d] += pg[ch][i];
-              acc[a.D + d] += pb[ch][i];
-            }
-          }
-        }
-      }
-    }
-    __syncthreads();
-  }
-  float *out = a.partials + (size_t)blockIdx.x * 2 * a.D;
-  for (int d = threadIdx.x; d < 2 * a.D; d += 256) out[d] = acc[d];
 }
 
+// backward, part 2: per-CTA partial sums of dgamma = sum_rows g * xhat and dbeta = sum_rows g.  Thread (tx, ty) owns the
+// 8 columns of chunk tx and walks the rows ty, ty + 4 * gridDim.x, ...: fully coalesced, no shuffles.
+constexpr int DGB_ROWS = 4;
+template <typename T>
+__global__ void __launch_bounds__(512) ln_bwd_dgb_kernel(const LnArgs a) {
+  extern __shared__ float acc[];  // [DGB_ROWS][2][D]
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int nch = a.D >> 3;
+  float pg[8], pb[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) pg[i] = pb[i] = 0.f;
+  if (tx < nch) {
+#pragma unroll 4
+    for (int row = blockIdx.x * DGB_ROWS + ty; row < a.R; row += gridDim.x * DGB_ROWS) {
+      const float mean = __ldg(a.mean + row), rstd = __ldg(a.rstd + row);
+      float g[8], s[8];
+      Chunk<T>::load(a.g, (size_t)row * nch + tx, g);
+      Chunk<T>::load(a.s_in, (size_t)row * nch + tx, s);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        pg[i] = fmaf(g[i], (s[i] - mean) * rstd, pg[i]);
+        pb[i] += g[i];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      acc[(ty * 2) * a.D + tx * 8 + i] = pg[i];
+      acc[(ty * 2 + 1) * a.D + tx * 8 + i] = pb[i];
+    }
+  }
+  __syncthreads();
+  float *out = a.partials + (size_t)blockIdx.x * 2 * a.D;
+  for (int d = ty * blockDim.x + tx; d < 2 * a.D; d += blockDim.x * DGB_ROWS) {
+    float v = 0.f;
+#pragma unroll
+    for (int r = 0; r < DGB_ROWS; ++r) v += acc[r * 2 * a.D + d];
+    out[d] = v;
+  }
+}
+
+// backward, part 3: fixed-order sum of the per-CTA partials; one CTA per 32 columns, the 8 warps split the partial rows
 __global__ void __launch_bounds__(256) ln_bwd_reduce_kernel(const float *partials, int nblk, int D, float *dgamma, float *dbeta) {
-  const int d = blockIdx.x * 256 + threadIdx.x;
-  if (d >= 2 * D) return;
+  __shared__ float red[8][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int d = blockIdx.x * 32 + lane;
   float s = 0.f;
-  for (int b = 0; b < nblk; ++b) s += partials[(size_t)b * 2 * D + d];
-  if (d < D) dgamma[d] = s; else dbeta[d - D] = s;
+  if (d < 2 * D)
+    for (int b = warp; b < nblk; b += 8) s += partials[(size_t)b * 2 * D + d];
+  red[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0 && d < 2 * D) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][lane];
+    if (d < D) dgamma[d] = t; else dbeta[d - D] = t;
+  }
 }
 
 constexpr int BWD_MAX_BLOCKS = 296;
@@ -271,13 +288,19 @@ int launch_fwd(const LnArgs &a, bool has_res, bool drop, cudaStream_t st) {
 template <typename T, int MAXCH>
 int launch_bwd(const LnArgs &a, bool drop, float *dgamma, float *dbeta, cudaStream_t st) {
   int grid = (a.R + 7) / 8;
-  if (grid > BWD_MAX_BLOCKS) grid = BWD_MAX_BLOCKS;
-  const size_t smem = (size_t)2 * a.D * sizeof(float);
-  if (drop) ln_bwd_kernel<T, MAXCH, true><<<grid, 256, smem, st>>>(a);
-  else ln_bwd_kernel<T, MAXCH, false><<<grid, 256, smem, st>>>(a);
+  if (grid > 148 * 8) grid = 148 * 8;
+  if (drop) ln_bwd_dx_kernel<T, MAXCH, true><<<grid, 256, 0, st>>>(a);
+  else ln_bwd_dx_kernel<T, MAXCH, false><<<grid, 256, 0, st>>>(a);
   int rc = sv::after_launch();
   if (rc) return rc;
-  ln_bwd_reduce_kernel<<<(2 * a.D + 255) / 256, 256, 0, st>>>(a.partials, grid, a.D, dgamma, dbeta);
+  int nblk = (a.R + DGB_ROWS * 4 - 1) / (DGB_ROWS * 4);  // >= 4 rows per thread before a CTA is added
+  if (nblk > BWD_MAX_BLOCKS) nblk = BWD_MAX_BLOCKS;
+  const int nch = a.D >> 3;
+  const dim3 block((unsigned)((nch + 31) / 32 * 32), DGB_ROWS);
+  ln_bwd_dgb_kernel<T><<<nblk, block, (size_t)DGB_ROWS * 2 * a.D * sizeof(float), st>>>(a);
+  rc = sv::after_launch();
+  if (rc) return rc;
+  ln_bwd_reduce_kernel<<<(2 * a.D + 31) / 32, 256, 0, st>>>(a.partials, nblk, a.D, dgamma, dbeta);
   return sv::after_launch();
 }
 

@@ -49,9 +49,25 @@ def _bert_output_forward(self, hidden_states, input_tensor):
     return self.LayerNorm(h, residual=input_tensor, dropout_p=self.dropout.p if self.training else 0.0)
 
 
+def _bert_self_attention_forward(self, hidden_states, attention_mask=None, past_key_values=None, **kwargs):
+    """BertSelfAttention through ops.attention (native tcgen05 forward / backward with in-kernel attention dropout on
+    CUDA bf16).  `attention_mask` is the padding mask HF prepared for its SDPA path: None, or (B,1,Lq,Lk) with True /
+    0.0 = attend (identical rows), from which the (B,Lk) key-padding mask is read back."""
+    q = ops.linear(hidden_states, self.query.weight, self.query.bias)
+    k = ops.linear(hidden_states, self.key.weight, self.key.bias)
+    v = ops.linear(hidden_states, self.value.weight, self.value.bias)
+    kpm = None
+    if attention_mask is not None:
+        row = attention_mask[:, 0, 0, :]
+        kpm = row.logical_not() if row.dtype == torch.bool else row < 0
+    out = ops.attention(q, k, v, self.num_attention_heads, key_padding_mask=kpm,
+                        dropout_p=self.dropout.p if self.training else 0.0)
+    return out, None
+
+
 def _fuse_bert_layer_norms(bert):
-    """Same modules, parameters and state_dict keys as the HF model; only the forward of the LayerNorms (and of the two
-    residual tails of every block) is routed to ops.layer_norm."""
+    """Same modules, parameters and state_dict keys as the HF model; only the forward of the LayerNorms, of the two
+    residual tails of every block (-> ops.layer_norm) and of the self-attention core (-> ops.attention) is re-routed."""
     import types
     from .modules.layers import LayerNorm
     for mod in bert.modules():
@@ -60,6 +76,8 @@ def _fuse_bert_layer_norms(bert):
     for layer in bert.encoder.layer:
         for tail in (layer.attention.output, layer.output):
             tail.forward = types.MethodType(_bert_output_forward, tail)
+        if layer.attention.self.attention_head_size == 64:
+            layer.attention.self.forward = types.MethodType(_bert_self_attention_forward, layer.attention.self)
 
 
 def no_decay_param_group(parameters, lr):

@@ -122,12 +122,12 @@ def attention(q, k, v, num_heads, key_padding_mask=None, dropout_p=0.0):
     key_padding_mask (B,Lk) bool, True = ignore (nn.MultiheadAttention convention)."""
     B, Lq, E = q.shape
     Lk, hd = k.shape[1], E // num_heads
-    if hd == 64 and Lk <= 256 and _native_ok(q, k, v):
+    if hd == 64 and Lk <= 384 and _native_ok(q, k, v):
         needs_grad = torch.is_grad_enabled() and (q.requires_grad or k.requires_grad or v.requires_grad)
         if not needs_grad and dropout_p == 0.0:
             from . import native
             return native.attention(q, k, v, num_heads, key_padding_mask=key_padding_mask)
-        if Lq <= 256:
+        if Lq <= 384:
             return _AttentionFn.apply(q, k, v, None, None, key_padding_mask, num_heads, 0, float(dropout_p),
                                       _next_dropout_seed() if dropout_p > 0.0 else 0)
     qh = q.view(B, Lq, num_heads, hd).transpose(1, 2)
@@ -143,8 +143,8 @@ def attention(q, k, v, num_heads, key_padding_mask=None, dropout_p=0.0):
 def spatial_attention(q, k, v, spatial_weights, pairwise_locs, n_head, spatial_n_head, key_padding_mask=None):
     """Dispatch: bf16 CUDA tensors with head dim 64 -> fused tcgen05 kernel (attention map not returned: every reference
     caller discards it); anything else -> the torch formulation below."""
-    if _native_ok(q, k, v) and q.shape[-1] // n_head == 64 and k.shape[1] <= 256:
-        fn = _AttentionFn if (spatial_n_head == n_head and q.shape[1] <= 256) else _SpatialAttentionRecomputeFn
+    if _native_ok(q, k, v) and q.shape[-1] // n_head == 64 and k.shape[1] <= 384:
+        fn = _AttentionFn if (spatial_n_head == n_head and q.shape[1] <= 384) else _SpatialAttentionRecomputeFn
         out = fn.apply(q, k, v, spatial_weights.float(), pairwise_locs.float(), key_padding_mask, n_head, spatial_n_head)
         return out, None
     return _spatial_attention_torch(q, k, v, spatial_weights, pairwise_locs, n_head, spatial_n_head, key_padding_mask)

@@ -10,7 +10,7 @@ def rand(*shape, seed=0, scale=1.0):
     return torch.randn(*shape, device="cuda", generator=g) * scale
 
 
-@pytest.mark.parametrize("Lq,Lk", [(80, 80), (130, 130), (80, 50), (50, 80), (50, 50), (32, 32), (1, 7), (129, 160), (300, 256), (17, 200)])
+@pytest.mark.parametrize("Lq,Lk", [(80, 80), (130, 130), (80, 50), (50, 80), (50, 50), (32, 32), (1, 7), (129, 160), (300, 256), (17, 200), (300, 300), (40, 384)])
 def test_plain_attention(Lq, Lk):
     from sceneverse_b200 import native, ops
     B, H, E = 3, 12, 768
@@ -110,7 +110,7 @@ def test_fused_cross_entropy_matches_torch(dtype):
     assert abs(float(l2) - float(want)) < 1e-5 and torch.isfinite(og.grad).all()
 
 
-@pytest.mark.parametrize("Lq,Lk", [(80, 80), (130, 130), (50, 80), (80, 50), (33, 7), (256, 200), (129, 65)])
+@pytest.mark.parametrize("Lq,Lk", [(80, 80), (130, 130), (50, 80), (80, 50), (33, 7), (256, 200), (129, 65), (300, 300), (384, 50)])
 def test_plain_attention_backward_native(Lq, Lk):
     from sceneverse_b200 import ops
     B, H, E = 3, 12, 768
@@ -160,7 +160,7 @@ def _dropout_keep(seed, B, H, Lq, Lk, p):
     return (u16 >= np.uint64(int(p * 65536.0 + 0.5))).reshape(B, H, Lq, Lk)
 
 
-@pytest.mark.parametrize("Lq,Lk", [(130, 130), (80, 50)])
+@pytest.mark.parametrize("Lq,Lk", [(130, 130), (80, 50), (300, 300)])
 def test_attention_dropout_forward_backward(Lq, Lk):
     """Attention-weight dropout inside the kernels: the mask is a pure function of (seed, b, h, i, j), so the torch
     reference can be fed exactly the same mask."""
