@@ -107,6 +107,12 @@ int sv_layer_norm_bwd(const void *g, const void *s, int io_bf16, int R, int D, c
                       float *dbeta, float *scratch, void *stream);
 int sv_layer_norm_scratch_floats(int D);
 
+/* Every in-kernel dropout mask (attention weights, fused LayerNorm) is a pure function of (seed, indices).  A captured
+ * CUDA graph freezes the by-value seed, so a process may register ONE device counter: each dropout launch then uses
+ * seed + *device_counter * odd_constant, read on the device at run time — increment the counter once per step (inside the
+ * graph) and every replay draws fresh masks while forward and backward of the same step still agree.  NULL unregisters. */
+int sv_dropout_seed_offset(const unsigned long long *device_counter);
+
 /* calc_pairwise_locs, 'center' relation (reference: modules/utils.py:38-87): centers (B,O,*) f32 with row stride
  * row_stride (>= 3 floats; xyz first) -> out (B,O,O,5) f32 = [dist/max_dist, dz/dist, dist2d/dist, dy/dist2d, dx/dist2d];
  * dist_norm = 0 keeps the raw distance in slot 0.  eps sits inside the square roots (1e-10 in the reference). */

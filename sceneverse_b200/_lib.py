@@ -92,6 +92,7 @@ _GPS_SIGS = {
     "sv_layer_norm_bwd": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_float, ctypes.c_ulonglong,
                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "sv_layer_norm_scratch_floats": [c_int],
+    "sv_dropout_seed_offset": [c_void_p],
     "sv_sa_mlp_param_bytes": [c_int],
     "sv_sa1_mlp_bf16": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
     "sv_sa2_mlp_bf16": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],

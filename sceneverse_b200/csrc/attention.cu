@@ -34,6 +34,7 @@ struct FwdArgs {
   uint32_t t16;                    // dropout threshold (DROP)
   float inv_keep;
   unsigned long long seed;
+  const unsigned long long *seed_offset;  // device counter added to the seed at run time (or null)
 };
 
 __device__ __forceinline__ float u2f(uint32_t x) { return __uint_as_float(x); }
@@ -116,7 +117,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
       gw.load(a.sw + ((size_t)b * a.Lq + qi) * (a.SH * 6) + (a.SH == 1 ? 0 : h) * 6);
       loc = a.locs + ((size_t)b * a.Lq + qi) * (size_t)a.Lk * 5;
     }
-    if (DROP) rk = drop_row_key(a.seed, ((unsigned long long)b * a.H + h) * a.Lq + qi);
+    if (DROP) rk = drop_row_key(attn::effective_seed(a.seed, a.seed_offset), ((unsigned long long)b * a.H + h) * a.Lq + qi);
     mbar_wait(&bars[2], ph_m);
     ph_m ^= 1u;
     fence_after_sync();
@@ -338,7 +339,7 @@ extern "C" int sv_attention_fwd_dropout_bf16(const void *q, long long q_bs, int 
   a.tmem_cols = pow2_cols(NK < 64 ? 64 : NK);
   a.t16 = drop_threshold(dropout_p);
   a.inv_keep = 1.0f / (1.0f - dropout_p);
-  a.seed = seed;
+  a.seed = seed; a.seed_offset = sv::g_seed_offset;
   CUtensorMap mq, mk, mv;
   int rc = make_map(&mq, q, B, Lq, H, q_rs, q_bs);
   if (rc) return rc;

@@ -29,6 +29,7 @@ struct BwdArgs {
   uint32_t t16;
   float inv_keep;
   unsigned long long seed;
+  const unsigned long long *seed_offset;  // device counter added to the seed at run time (or null)
 };
 
 __device__ __forceinline__ float u2f(uint32_t x) { return __uint_as_float(x); }
@@ -117,7 +118,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mR1, const __grid_constant__
       const size_t r = ((size_t)b * a.H + h) * a.Lq + c;
       lse2s[c] = live ? a.lse[r] * LOG2E : INFINITY;
       Dv[c] = live ? a.dvec[r] : 0.f;
-      rks[c] = DROP ? drop_row_key(a.seed, r) : 0u;
+      rks[c] = DROP ? drop_row_key(attn::effective_seed(a.seed, a.seed_offset), r) : 0u;
       if (GATED) {
         const float *w = a.sw + ((size_t)b * a.Lq + (live ? c : 0)) * (a.H * 6) + h * 6;
 #pragma unroll
@@ -167,7 +168,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mR1, const __grid_constant__
           gw.load(a.sw + ((size_t)b * a.Lq + ri) * (a.H * 6) + h * 6);
           loc = a.locs + ((size_t)b * a.Lq + ri) * (size_t)a.Lk * 5;
         }
-        if (DROP) rk = drop_row_key(a.seed, r);
+        if (DROP) rk = drop_row_key(attn::effective_seed(a.seed, a.seed_offset), r);
       }
     } else {
       klive = rlive && !(a.kpm != nullptr && a.kpm[(size_t)b * a.Lk + ri]);
@@ -449,7 +450,7 @@ extern "C" int sv_attention_bwd_dropout_bf16(const void *q, long long q_bs, int 
   a.dsw = d_spatial_w; a.dvec = dvec;
   a.t16 = drop_threshold(dropout_p);
   a.inv_keep = 1.0f / (1.0f - dropout_p);
-  a.seed = seed;
+  a.seed = seed; a.seed_offset = sv::g_seed_offset;
   CUtensorMap mq, mk, mv, mo;
   int rc = make_map(&mq, q, B, Lq, H, q_rs, q_bs);
   if (rc) return rc;

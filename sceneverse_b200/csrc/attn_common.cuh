@@ -127,6 +127,11 @@ __host__ __device__ __forceinline__ uint32_t drop_row_key(unsigned long long see
   x ^= x >> 33;
   return (uint32_t)x;
 }
+// seed actually used by a launch: the by-value seed plus the run-time device counter (fresh masks on every replay of a
+// captured CUDA graph, whose kernel arguments are frozen)
+__device__ __forceinline__ unsigned long long effective_seed(unsigned long long seed, const unsigned long long *offset) {
+  return offset != nullptr ? seed + __ldg(offset) * 0xD1B54A32D192ED03ull : seed;
+}
 __host__ __device__ __forceinline__ uint32_t drop_pair_hash(uint32_t row_key, uint32_t jpair) {
   uint32_t h = row_key ^ (jpair * 0x9E3779B1u);
   h ^= h >> 16;

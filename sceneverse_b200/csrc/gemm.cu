@@ -4,8 +4,8 @@
 //
 //   C[M,N] = epilogue( A[M,K] (bf16, row-major)  x  B[N,K]^T (bf16, row-major = nn.Linear weight layout) )
 //
-// Roles (192 threads): warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator + MMA issuer (one lane),
-// warps 2..5 = epilogue (one thread per accumulator row / TMEM lane).  Operand tiles travel global -> shared by TMA
+// Roles (320 threads): warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator + MMA issuer (one lane),
+// warps 2..9 = epilogue (two warps per TMEM lane quadrant, each thread one accumulator row x half of the columns).  Operand tiles travel global -> shared by TMA
 // (cp.async.bulk.tensor.2d, one box of [rows x 64 elements] = 128-byte rows, SWIZZLE_128B, read back by the tensor core
 // through a SWIZZLE_128B K-major UMMA descriptor) through a 4-stage mbarrier ring; accumulators are double-buffered
 // in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.  Out-of-bounds rows / columns / K are zero-filled by
@@ -22,6 +22,7 @@ namespace {
 using namespace tc05;
 
 constexpr int BM = 128, BK = 64, STAGES = 4;
+constexpr int STG_BYTES = 32 * 80;  // per epilogue warp: 32 rows x (64 B + 16 B pad); also holds the [32][17] f32 row-max scratch
 
 struct GemmArgs {
   int M, N, K;
@@ -46,7 +47,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
 template <int BN>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GemmArgs g) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int A_STAGE = BM * BK * 2, B_STAGE = BN * BK * 2;
@@ -57,7 +58,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
   uint64_t *acc_full = empty + STAGES;   // [2]
   uint64_t *acc_empty = acc_full + 2;    // [2]
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
-  float *stage = reinterpret_cast<float *>(tmem_slot + 4);  // [4 warps][32][33] transpose scratch (row-max epilogue)
+  float *stage = reinterpret_cast<float *>(tmem_slot + 4);  // [8 warps][STG_BYTES] store staging / row-max transpose scratch
+  float *sbias = stage + 8 * STG_BYTES / 4;                     // [2][BN] bias slice of the tile, double-buffered
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_m = (g.M + BM - 1) / BM, tiles_n = (g.N + BN - 1) / BN;
@@ -71,7 +73,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(acc_full + b, 1);
-      mbar_init(acc_empty + b, 128);
+      mbar_init(acc_empty + b, 256);
     }
     mbar_fence_init();
   }
@@ -121,95 +123,134 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       }
     }
   } else {
-    // ------------------------------- epilogue (warps 2..5) -------------------------------
-    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    // ------------------------------- epilogue (warps 2..9) -------------------------------
+    // Two warps per TMEM lane quadrant, each taking half of the tile's columns.  Per tile the bias slice is staged once in
+    // shared memory (double-buffered with the accumulator), TMEM loads run one 32-column chunk ahead of the math.
+    const int q = warp & 3;             // TMEM lane quadrant this warp may access (hardware rule: warp id % 4)
+    const int half = (warp - 2) >> 2;   // which half of the BN columns
+    const int et = threadIdx.x - 64;    // 0..255
     const int row_in_tile = q * 32 + lane;
+    constexpr int NCHUNK = BN / 64;     // 32-column chunks per warp
     uint32_t tl = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tl) {
       const int b = tl & 1;
       const int m0 = (t % tiles_m) * BM, n0 = (t / tiles_m) * BN;
       const int row = m0 + row_in_tile;
+      float *sb = sbias + b * BN;
+      if (et < BN) sb[et] = (g.bias != nullptr && n0 + et < g.N) ? __ldg(g.bias + n0 + et) : 0.f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // bias visible; everybody is done with the tile before last
       mbar_wait(acc_full + b, (tl >> 1) & 1u);
       fence_after_sync();
-      const uint32_t taddr = tmem + b * BN + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        float v[32];
-        tmem_ld32(taddr + c0, v);
+      const uint32_t taddr = tmem + b * BN + half * (BN / 2) + ((uint32_t)(q * 32) << 16);
+      uint32_t rr[2][32];
+      tmem_ld32_async(taddr, rr[0]);
+#pragma unroll
+      for (int ci = 0; ci < NCHUNK; ++ci) {
+        uint32_t(&cur)[32] = rr[ci & 1];
+        tmem_wait32(cur);
+        if (ci + 1 < NCHUNK) tmem_ld32_async(taddr + (ci + 1) * 32, rr[(ci + 1) & 1]);
+        const int c0 = half * (BN / 2) + ci * 32;
         const int col0 = n0 + c0;
         if (col0 < g.N) {
+        float v[32];
+        const float4 *b4 = reinterpret_cast<const float4 *>(sb + c0);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float x = v[i];
-            if (g.bias != nullptr && col0 + i < g.N) x += __ldg(g.bias + col0 + i);  // warp-uniform address: one broadcast
-            if (g.act == 1) x = fmaxf(x, 0.f);
-            else if (g.act == 2) x = gelu_erf(x);
-            v[i] = x;
+        for (int i = 0; i < 8; ++i) {
+          const float4 bb = b4[i];
+          v[4 * i] = __uint_as_float(cur[4 * i]) + bb.x;
+          v[4 * i + 1] = __uint_as_float(cur[4 * i + 1]) + bb.y;
+          v[4 * i + 2] = __uint_as_float(cur[4 * i + 2]) + bb.z;
+          v[4 * i + 3] = __uint_as_float(cur[4 * i + 3]) + bb.w;
+        }
+        if (g.act == 1) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+        } else if (g.act == 2) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+        }
+        if (g.rowmax == 16) {
+          // max over the 16 rows of each half-warp (16 consecutive rows = the 16 points of one cloud): 16 columns at a
+          // time go through a per-warp [32][17] transpose scratch; lanes 0-15 reduce rows 0-15, lanes 16-31 rows 16-31
+          float *tp = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(stage) + (warp - 2) * STG_BYTES);
+          const int l16 = lane & 15, grp = lane >> 4;
+          const int wrow0 = m0 + q * 32;  // first accumulator row of this warp
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) tp[lane * 17 + i] = row < g.M ? v[hh * 16 + i] : -INFINITY;
+            __syncwarp();
+            float mx = -INFINITY;
+#pragma unroll
+            for (int r2 = 0; r2 < 16; ++r2) mx = fmaxf(mx, tp[(grp * 16 + r2) * 17 + l16]);
+            __syncwarp();
+            const int col = col0 + hh * 16 + l16;
+            if (col < g.N && wrow0 + grp * 16 < g.M) {
+              const size_t orow = (size_t)(wrow0 >> 4) + grp;
+              if (g.out_f32) reinterpret_cast<float *>(g.out)[orow * g.ldo + col] = mx;
+              else reinterpret_cast<__nv_bfloat16 *>(g.out)[orow * g.ldo + col] = __float2bfloat16_rn(mx);
+            }
           }
-          if (g.rowmax == 16) {
-            // max over the 16 rows of each half-warp (16 consecutive rows = the 16 points of one cloud): the warp
-            // transposes its 32x32 chunk through shared memory so that lane i reduces column i of both groups
-            float *tp = stage + (warp - 2) * (32 * 33);
+        } else {
+          // Coalesced stores: the warp's 32 x 32 chunk goes through a per-warp [32][80 B] staging buffer (one row per
+          // lane in, 8 rows x 64 B per store instruction out), so a store instruction touches 8 lines instead of 32.
+          const bool full32 = col0 + 32 <= g.N;
+          uint8_t *stg = reinterpret_cast<uint8_t *>(stage) + (warp - 2) * STG_BYTES;
+          const int wrow0 = m0 + q * 32;
+          const int sr = lane >> 2, seg = lane & 3;
+          const bool vec_ok = full32 && g.residual == nullptr && (reinterpret_cast<uintptr_t>(g.out) & 15) == 0;
+          if (g.out_f32) {
+            float *ob = reinterpret_cast<float *>(g.out);
+            if (vec_ok && (g.ldo & 3) == 0 && (col0 & 3) == 0) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) tp[lane * 33 + i] = row < g.M ? v[i] : -INFINITY;
-            __syncwarp();
-            float ga = -INFINITY, gb = -INFINITY;
+              for (int hh = 0; hh < 2; ++hh) {
 #pragma unroll
-            for (int rr = 0; rr < 16; ++rr) {
-              ga = fmaxf(ga, tp[rr * 33 + lane]);
-              gb = fmaxf(gb, tp[(rr + 16) * 33 + lane]);
-            }
-            __syncwarp();
-            const int wrow0 = m0 + q * 32;  // first accumulator row of this warp
-            const int col = col0 + lane;
-            if (col < g.N) {
-              const size_t orow = (size_t)(wrow0 >> 4);
-              if (wrow0 < g.M) {
-                if (g.out_f32) reinterpret_cast<float *>(g.out)[orow * g.ldo + col] = ga;
-                else reinterpret_cast<__nv_bfloat16 *>(g.out)[orow * g.ldo + col] = __float2bfloat16_rn(ga);
-              }
-              if (wrow0 + 16 < g.M) {
-                if (g.out_f32) reinterpret_cast<float *>(g.out)[(orow + 1) * g.ldo + col] = gb;
-                else reinterpret_cast<__nv_bfloat16 *>(g.out)[(orow + 1) * g.ldo + col] = __float2bfloat16_rn(gb);
-              }
-            }
-          } else if (row < g.M) {
-            const bool full32 = col0 + 32 <= g.N;
-            if (g.out_f32) {
-              float *o = reinterpret_cast<float *>(g.out) + (size_t)row * g.ldo + col0;
-              const float *r = g.residual ? reinterpret_cast<const float *>(g.residual) + (size_t)row * g.ldo + col0 : nullptr;
-              if (full32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+                for (int k = 0; k < 4; ++k)
+                  *reinterpret_cast<float4 *>(stg + lane * 80 + k * 16) =
+                      make_float4(v[hh * 16 + 4 * k], v[hh * 16 + 4 * k + 1], v[hh * 16 + 4 * k + 2], v[hh * 16 + 4 * k + 3]);
+                __syncwarp();
 #pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                  float4 w = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                  if (r) {
-                    const float4 rr = *reinterpret_cast<const float4 *>(r + i);
-                    w.x += rr.x; w.y += rr.y; w.z += rr.z; w.w += rr.w;
-                  }
-                  *reinterpret_cast<float4 *>(o + i) = w;
+                for (int it = 0; it < 4; ++it) {
+                  const int r = it * 8 + sr;
+                  const float4 w = *reinterpret_cast<const float4 *>(stg + r * 80 + seg * 16);
+                  if (wrow0 + r < g.M)
+                    *reinterpret_cast<float4 *>(ob + (size_t)(wrow0 + r) * g.ldo + col0 + hh * 16 + seg * 4) = w;
                 }
-              } else {
-                for (int i = 0; i < 32 && col0 + i < g.N; ++i) o[i] = v[i] + (r ? r[i] : 0.f);
+                __syncwarp();
               }
-            } else {
-              __nv_bfloat16 *o = reinterpret_cast<__nv_bfloat16 *>(g.out) + (size_t)row * g.ldo + col0;
+            } else if (row < g.M) {
+              float *o = ob + (size_t)row * g.ldo + col0;
+              const float *r = g.residual ? reinterpret_cast<const float *>(g.residual) + (size_t)row * g.ldo + col0 : nullptr;
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (col0 + i < g.N) o[i] = v[i] + (r ? r[i] : 0.f);
+            }
+          } else {
+            __nv_bfloat16 *ob = reinterpret_cast<__nv_bfloat16 *>(g.out);
+            if (vec_ok && (g.ldo & 7) == 0 && (col0 & 7) == 0) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                *reinterpret_cast<uint4 *>(stg + lane * 80 + k * 16) =
+                    make_uint4(pack_bf16(v[8 * k], v[8 * k + 1]), pack_bf16(v[8 * k + 2], v[8 * k + 3]),
+                               pack_bf16(v[8 * k + 4], v[8 * k + 5]), pack_bf16(v[8 * k + 6], v[8 * k + 7]));
+              __syncwarp();
+#pragma unroll
+              for (int it = 0; it < 4; ++it) {
+                const int r = it * 8 + sr;
+                const uint4 w = *reinterpret_cast<const uint4 *>(stg + r * 80 + seg * 16);
+                if (wrow0 + r < g.M) *reinterpret_cast<uint4 *>(ob + (size_t)(wrow0 + r) * g.ldo + col0 + seg * 8) = w;
+              }
+              __syncwarp();
+            } else if (row < g.M) {
+              __nv_bfloat16 *o = ob + (size_t)row * g.ldo + col0;
               const __nv_bfloat16 *r =
                   g.residual ? reinterpret_cast<const __nv_bfloat16 *>(g.residual) + (size_t)row * g.ldo + col0 : nullptr;
-              if (full32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
 #pragma unroll
-                for (int i = 0; i < 32; i += 8) {
-                  float a[8];
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) a[j] = v[i + j] + (r ? __bfloat162float(r[i + j]) : 0.f);
-                  *reinterpret_cast<uint4 *>(o + i) =
-                      make_uint4(pack_bf16(a[0], a[1]), pack_bf16(a[2], a[3]), pack_bf16(a[4], a[5]), pack_bf16(a[6], a[7]));
-                }
-              } else {
-                for (int i = 0; i < 32 && col0 + i < g.N; ++i)
-                  o[i] = __float2bfloat16_rn(v[i] + (r ? __bfloat162float(r[i]) : 0.f));
-              }
+              for (int i = 0; i < 32; ++i)
+                if (col0 + i < g.N) o[i] = __float2bfloat16_rn(v[i] + (r ? __bfloat162float(r[i]) : 0.f));
             }
           }
+        }
         }
       }
       fence_before_sync();
@@ -253,7 +294,7 @@ int make_map(CUtensorMap *map, const void *ptr, int rows, int K, int ld, int box
 
 template <int BN>
 int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mb, const GemmArgs &g, cudaStream_t st) {
-  constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + (2 * STAGES + 4) * 8 + 16 + 4 * 32 * 33 * 4;
+  constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + (2 * STAGES + 4) * 8 + 16 + 8 * STG_BYTES + 2 * BN * 4;
   auto kern = gemm_kernel<BN>;
   static int sms_of_dev[64] = {0};  // also marks "attribute set on this device" (one-time host work per device)
   int dev = 0;
@@ -269,7 +310,7 @@ int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mb, const GemmArgs &g,
   const int sms = sms_of_dev[dev];
   const int tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN);
   const int grid = tiles < sms ? tiles : sms;
-  kern<<<grid, 192, smem, st>>>(ma, mb, g);
+  kern<<<grid, 320, smem, st>>>(ma, mb, g);
   return sv::after_launch();
 }
 

@@ -32,6 +32,7 @@ struct LnArgs {
   uint32_t t16;
   float inv_keep;
   unsigned long long seed;
+  const unsigned long long *seed_offset;  // device counter added to the seed at run time (or null)
 };
 
 template <typename T>
@@ -104,7 +105,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const LnArgs a) {
     const size_t base8 = (size_t)row * nch;
     float v[MAXCH][8];
     uint32_t rk = 0;
-    if (DROP) rk = drop_row_key(a.seed, (unsigned long long)row);
+    if (DROP) rk = drop_row_key(attn::effective_seed(a.seed, a.seed_offset), (unsigned long long)row);
     float sum = 0.f;
 #pragma unroll
     for (int ch = 0; ch < MAXCH; ++ch) {
@@ -194,7 +195,7 @@ __global__ void __launch_bounds__(256) ln_bwd_dx_kernel(const LnArgs a) {
     s1 = warp_sum(s1) * invD;
     s2 = warp_sum(s2) * invD;
     uint32_t rk = 0;
-    if (DROP) rk = drop_row_key(a.seed, (unsigned long long)row);
+    if (DROP) rk = drop_row_key(attn::effective_seed(a.seed, a.seed_offset), (unsigned long long)row);
 #pragma unroll
     for (int ch = 0; ch < MAXCH; ++ch) {
       const int c = lane + 32 * ch;
@@ -323,7 +324,7 @@ extern "C" int sv_layer_norm_fwd(const void *x, const void *residual, int io_bf1
   LnArgs a{};
   a.x = x; a.res = residual; a.y = y; a.s_out = s; a.gamma = gamma; a.beta = beta; a.mean = mean; a.rstd = rstd;
   a.R = R; a.D = D; a.eps = eps; a.t16 = attn::drop_threshold(dropout_p); a.inv_keep = 1.0f / (1.0f - dropout_p);
-  a.seed = seed;
+  a.seed = seed; a.seed_offset = sv::g_seed_offset;
   cudaStream_t st = (cudaStream_t)stream;
   const int maxch = (D + 255) / 256;
   const bool d = a.t16 != 0;
@@ -353,7 +354,7 @@ extern "C" int sv_layer_norm_bwd(const void *g, const void *s, int io_bf16, int 
   LnArgs a{};
   a.g = g; a.s_in = s; a.ds = ds; a.dx = dx; a.gamma = gamma; a.mean = const_cast<float *>(mean);
   a.rstd = const_cast<float *>(rstd); a.partials = scratch;
-  a.R = R; a.D = D; a.t16 = attn::drop_threshold(dropout_p); a.inv_keep = 1.0f / (1.0f - dropout_p); a.seed = seed;
+  a.R = R; a.D = D; a.t16 = attn::drop_threshold(dropout_p); a.inv_keep = 1.0f / (1.0f - dropout_p); a.seed = seed; a.seed_offset = sv::g_seed_offset;
   cudaStream_t st = (cudaStream_t)stream;
   const int maxch = (D + 255) / 256;
   const bool d = a.t16 != 0;

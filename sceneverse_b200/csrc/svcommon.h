@@ -11,6 +11,8 @@ namespace sv {
 
 extern std::atomic<unsigned long long> g_launches;
 extern thread_local int t_last_cuda_error;
+// device counter added (on the device, at run time) to the seed of every in-kernel dropout mask; see sv_dropout_seed_offset
+extern const unsigned long long *g_seed_offset;
 
 // Call after every <<<>>>: records the launch, maps a launch failure to SV_ERR_CUDA.
 inline int after_launch() {

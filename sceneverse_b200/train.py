@@ -36,7 +36,12 @@ class StepModule(nn.Module):
 
 
 class PretrainStep:
-    def __init__(self, cfg, device, total_steps=100000, dtype=torch.bfloat16, ddp=None, seed=0):
+    def __init__(self, cfg, device, total_steps=100000, dtype=torch.bfloat16, ddp=None, seed=0, cuda_graph=False):
+        """cuda_graph=True (single process, CUDA): after a few eager steps the whole step — forward, losses, backward,
+        gradient clipping and AdamW — is captured once into a CUDA graph and replayed from static input buffers; the host
+        then issues one graph launch per step instead of ~2000 kernel launches.  Dropout stays random: torch's own dropout
+        through the graph-registered generator, the in-kernel masks through the device step counter registered with
+        sv_dropout_seed_offset."""
         torch.manual_seed(seed)
         self.cfg = M.to_cfg(cfg)
         self.device = torch.device(device)
@@ -47,14 +52,28 @@ class PretrainStep:
                        'lr': self.cfg.solver.lr})
         kw = dict(self.cfg.solver.optim.args)
         kw["betas"] = tuple(kw.get("betas", (0.9, 0.999)))
-        self.optimizer = torch.optim.AdamW(groups, lr=self.cfg.solver.lr, fused=self.device.type == "cuda", **kw)
+        self.use_ddp = ddp if ddp is not None else (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1)
+        self.graph_mode = bool(cuda_graph) and self.device.type == "cuda" and not self.use_ddp
         warm = self.cfg.solver.sched.args.warmup_steps * self.cfg.num_gpu
         mr = self.cfg.solver.sched.args.get("minimum_ratio", 1e-5)
-        self.scheduler = torch.optim.lr_scheduler.LambdaLR(
-            self.optimizer, lambda s: M.warmup_cosine(s, warm, total_steps, minimum_ratio=mr))
+        self._lr_lambda = lambda s: M.warmup_cosine(s, warm, total_steps, minimum_ratio=mr)
+        if self.graph_mode:
+            # capturable AdamW reads lr from a device tensor; the warm-up/cosine schedule fills it from the host per step
+            self._base_lrs = [float(g.get('lr', self.cfg.solver.lr)) for g in groups]
+            for g in groups:
+                g['lr'] = torch.tensor(float(g.get('lr', self.cfg.solver.lr)) * self._lr_lambda(0), device=self.device)
+            self.optimizer = torch.optim.AdamW(groups, fused=True, capturable=True, **kw)
+            self.scheduler = None
+            self._sched_step = 0
+            self._step_counter = torch.zeros(1, dtype=torch.int64, device=self.device)
+            from . import _lib
+            _lib.check(_lib.gps(), _lib.gps().sv_dropout_seed_offset(self._step_counter.data_ptr()), "sv_dropout_seed_offset")
+            self.graph = self.static_batch = self.static_loss = None
+        else:
+            self.optimizer = torch.optim.AdamW(groups, lr=self.cfg.solver.lr, fused=self.device.type == "cuda", **kw)
+            self.scheduler = torch.optim.lr_scheduler.LambdaLR(self.optimizer, self._lr_lambda)
         self.grad_norm = self.cfg.solver.get("grad_norm")
         self.ddp = None
-        self.use_ddp = ddp if ddp is not None else (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1)
         self.probed = False
         self.module.train()
 
@@ -83,8 +102,59 @@ class PretrainStep:
     def parameters(self):
         return [p for p in self.module.parameters() if p.requires_grad]
 
+    # ---- CUDA-graph path ---------------------------------------------------------------------------------------------
+    def _raw_step(self):
+        self._step_counter.add_(1)
+        self.optimizer.zero_grad(set_to_none=False)
+        with torch.autocast(self.device.type, dtype=self.dtype, enabled=self.dtype != torch.float32):
+            total, _ = self.module(dict(self.static_batch))
+        total.backward()
+        if self.grad_norm is not None:
+            torch.nn.utils.clip_grad_norm_(self.parameters(), self.grad_norm, foreach=True)
+        self.optimizer.step()
+        return total.detach()
+
+    def _advance_lr(self):
+        self._sched_step += 1
+        f = self._lr_lambda(self._sched_step)
+        for g, base in zip(self.optimizer.param_groups, self._base_lrs):
+            g['lr'].fill_(base * f)
+
+    def _capture(self, data_dict):
+        self.static_batch = {k: v.clone() for k, v in data_dict.items() if torch.is_tensor(v)}
+        cur = torch.cuda.current_stream(self.device)
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(3):          # real optimisation steps: allocates grads / optimizer state outside the graph pool
+                self._raw_step()
+                self._advance_lr()
+        cur.wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        from . import _lib
+        n0 = _lib.launch_count()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.static_loss = self._raw_step()
+        self.native_launches_per_step = _lib.launch_count() - n0   # native kernel nodes replayed per step
+
+    def _graph_step(self, data_dict):
+        if not self.probed:
+            self._probe_unused(data_dict)
+        if self.graph is None:
+            self._capture(data_dict)
+        for k, dst in self.static_batch.items():
+            src = data_dict[k]
+            if src.data_ptr() != dst.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        self._advance_lr()
+        return self.static_loss
+
     def step(self, data_dict):
         """data_dict: tensors already on self.device. Returns the (detached) total loss tensor — no host sync."""
+        if self.graph_mode:
+            return self._graph_step(data_dict)
         if not self.probed:
             self._probe_unused(data_dict)
         net = self.ddp if self.ddp is not None else self.module

@@ -269,3 +269,24 @@ def test_padded_vocab_head_and_cross_entropy():
     # the plain slice view still works for consumers that do not know about the padding
     loss2 = F.cross_entropy(ops.padded_vocab_linear(h.detach(), W.detach(), b.detach()).float(), labels, ignore_index=-1)
     assert abs(float(loss2) - float(ref)) < 5e-3 * max(1.0, abs(float(ref)))
+
+
+def test_dropout_seed_offset_counter_changes_masks():
+    """sv_dropout_seed_offset: with a registered device counter the same (frozen) seed gives a new mask whenever the
+    counter changes and the same mask when it does not — what a replayed CUDA graph relies on."""
+    from sceneverse_b200 import native, _lib
+    B, H, L, E = 2, 12, 64, 768
+    q, k, v = (rand(B, L, E, seed=i).bfloat16() for i in (1, 2, 3))
+    counter = torch.zeros(1, dtype=torch.int64, device="cuda")
+    lib = _lib.gps()
+    try:
+        assert lib.sv_dropout_seed_offset(counter.data_ptr()) == 0
+        a = native.attention(q, k, v, H, dropout_p=0.2, seed=77).clone()
+        b = native.attention(q, k, v, H, dropout_p=0.2, seed=77).clone()
+        counter.add_(1)
+        c = native.attention(q, k, v, H, dropout_p=0.2, seed=77).clone()
+        assert torch.equal(a, b) and not torch.equal(a, c)
+    finally:
+        lib.sv_dropout_seed_offset(None)
+    d = native.attention(q, k, v, H, dropout_p=0.2, seed=77)
+    assert torch.equal(a, d)                                               # counter 0 == no counter
