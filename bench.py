@@ -298,8 +298,11 @@ def main():
     h2d_bytes = sum(v.numel() * v.element_size() for v in pinned[0].values())
     tf = weights.synthetic_tensor("text_features", (607, 768))
     ps = train.PretrainStep(M.pretrain_config(world, text_features=tf), device, dtype=torch.bfloat16, seed=1234,
-                            cuda_graph=(world == 1 and not args.no_graph))
+                            cuda_graph=not args.no_graph)
     config["cuda_graph"] = bool(ps.graph_mode)
+    if world > 1:
+        config["dp_impl"] = ("graph(fwd+bwd) + one flat NCCL all-reduce + graph(clip+AdamW)" if ps.dp_graph
+                             else "torch DDP (bucketed NCCL all-reduce overlapped with backward)")
     host_loss = torch.zeros((), dtype=torch.float32).pin_memory()
 
     def step_resident(i):
@@ -389,7 +392,8 @@ def main():
                                       "norm_allgather_kernel (N > 1: contrastive exchange over NVLink peer memory)"],
            "library_ops_in_step": ["plain linears forward/backward (cuBLAS)", "FFN dropout / GELU / embedding (ATen)",
                                    "AdamW + gradient clipping (torch fused / foreach)", "gradient all-reduce (NCCL via DDP, N > 1)"],
-           "launch": "whole step captured in one CUDA graph" if ps.graph_mode else "eager"}
+           "launch": ("CUDA graphs (forward+backward | NCCL all-reduce | clip+AdamW)" if ps.dp_graph else
+                      "whole step captured in one CUDA graph" if ps.graph_mode else "eager")}
     if rt is not None:
         out["roofline"], out["roofline_pointops"] = rt, rp
     if not args.no_cpu_baseline:

@@ -139,6 +139,11 @@ int sv_cross_entropy_fwd_bwd_strided(const void *logits, long long row_stride, i
 int sv_normalize_allgather_f32(const float *a, const float *b, int n, int D, void *const *peer_bufs,
                                void *const *peer_signals, unsigned *done_counter, int world, int rank, unsigned epoch,
                                void *stream);
+/* same exchange with the epoch kept in device memory (*epoch_dev, zero-initialised, one word per exchange object): the
+ * launch uses *epoch_dev + 1 and stores it back on completion, so a captured CUDA graph (frozen arguments) can replay it */
+int sv_normalize_allgather_dev_f32(const float *a, const float *b, int n, int D, void *const *peer_bufs,
+                                   void *const *peer_signals, unsigned *done_counter, int world, int rank,
+                                   unsigned *epoch_dev, void *stream);
 
 #ifdef __cplusplus
 }

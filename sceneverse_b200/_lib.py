@@ -73,6 +73,8 @@ _GPS_SIGS = {
                                          c_void_p, c_void_p, ctypes.c_longlong, c_void_p],
     "sv_normalize_allgather_f32": [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                    ctypes.c_uint, c_void_p],
+    "sv_normalize_allgather_dev_f32": [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                       c_void_p, c_void_p],
     "sv_attention_fwd_lse_bf16": [c_void_p, ctypes.c_longlong, c_int, c_void_p, ctypes.c_longlong, c_int, c_void_p,
                                   ctypes.c_longlong, c_int, c_void_p, ctypes.c_longlong, c_int, c_void_p, c_void_p, c_int,
                                   c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p],

@@ -24,22 +24,26 @@ class FusedNormGather:
         self.peer_bufs = torch.tensor(ptrs, dtype=torch.int64, device=device)
         self.peer_sigs = torch.tensor([p + 4 * data_floats for p in ptrs], dtype=torch.int64, device=device)
         self.done = torch.zeros(1, dtype=torch.int32, device=device)
-        self.epoch = 0
+        self.epoch_dev = torch.zeros(1, dtype=torch.int32, device=device)  # the kernel's own epoch word (graph-replay safe)
+        self.epoch = 0                                                       # host mirror: selects the parity of the views
         torch.cuda.synchronize(device)
         dist.barrier(self.group)  # every rank's buffer (incl. signal words) is zeroed before the first exchange
 
     def __call__(self, a, b):
-        """a, b: (n,D) -> (normalize(a) gathered (world*n,D), normalize(b) gathered), views of the symmetric buffer."""
+        """a, b: (n,D) -> (normalize(a) gathered (world*n,D), normalize(b) gathered), views of the symmetric buffer.
+        The views alternate between the two parity halves of the buffer call by call; inside a replayed CUDA graph the
+        parity of a call site is the one it had at capture, which matches the device epoch as long as the number of
+        exchanges per replay is even (two between-batch losses in the pre-training configuration)."""
         a = a.detach().float().contiguous()
         b = b.detach().float().contiguous()
         assert a.shape == (self.n, self.D) and b.shape == (self.n, self.D)
         self.epoch += 1
         lib = _lib.gps()
         with torch.cuda.device(a.device):
-            st = lib.sv_normalize_allgather_f32(a.data_ptr(), b.data_ptr(), self.n, self.D, self.peer_bufs.data_ptr(),
-                                                self.peer_sigs.data_ptr(), self.done.data_ptr(), self.world, self.rank,
-                                                self.epoch, torch.cuda.current_stream(a.device).cuda_stream)
-        _lib.check(lib, st, "sv_normalize_allgather_f32")
+            st = lib.sv_normalize_allgather_dev_f32(a.data_ptr(), b.data_ptr(), self.n, self.D, self.peer_bufs.data_ptr(),
+                                                    self.peer_sigs.data_ptr(), self.done.data_ptr(), self.world, self.rank,
+                                                    self.epoch_dev.data_ptr(), torch.cuda.current_stream(a.device).cuda_stream)
+        _lib.check(lib, st, "sv_normalize_allgather_dev_f32")
         wn = self.world * self.n
         base = (self.epoch & 1) * 2 * wn * self.D
         ga = self.buf[base: base + wn * self.D].view(wn, self.D)

@@ -53,7 +53,13 @@ class PretrainStep:
         kw = dict(self.cfg.solver.optim.args)
         kw["betas"] = tuple(kw.get("betas", (0.9, 0.999)))
         self.use_ddp = ddp if ddp is not None else (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1)
-        self.graph_mode = bool(cuda_graph) and self.device.type == "cuda" and not self.use_ddp
+        # cuda_graph with several ranks: no DDP wrapper — graph A (forward + losses + backward into one flat gradient
+        # buffer), ONE eager NCCL all-reduce (mean) of that buffer, graph B (clipping + AdamW).  No collective is captured;
+        # the contrastive exchange inside graph A is the native peer-memory kernel with a device-resident epoch.
+        self.graph_mode = bool(cuda_graph) and self.device.type == "cuda"
+        self.dp_graph = self.graph_mode and self.use_ddp
+        if self.dp_graph:
+            self.use_ddp = False
         warm = self.cfg.solver.sched.args.warmup_steps * self.cfg.num_gpu
         mr = self.cfg.solver.sched.args.get("minimum_ratio", 1e-5)
         self._lr_lambda = lambda s: M.warmup_cosine(s, warm, total_steps, minimum_ratio=mr)
@@ -68,7 +74,7 @@ class PretrainStep:
             self._step_counter = torch.zeros(1, dtype=torch.int64, device=self.device)
             from . import _lib
             _lib.check(_lib.gps(), _lib.gps().sv_dropout_seed_offset(self._step_counter.data_ptr()), "sv_dropout_seed_offset")
-            self.graph = self.static_batch = self.static_loss = None
+            self.graph = self.graph_opt = self.static_batch = self.static_loss = self.flat_grads = None
         else:
             self.optimizer = torch.optim.AdamW(groups, lr=self.cfg.solver.lr, fused=self.device.type == "cuda", **kw)
             self.scheduler = torch.optim.lr_scheduler.LambdaLR(self.optimizer, self._lr_lambda)
@@ -103,16 +109,28 @@ class PretrainStep:
         return [p for p in self.module.parameters() if p.requires_grad]
 
     # ---- CUDA-graph path ---------------------------------------------------------------------------------------------
-    def _raw_step(self):
+    def _raw_fwd_bwd(self):
         self._step_counter.add_(1)
-        self.optimizer.zero_grad(set_to_none=False)
+        if self.flat_grads is not None:
+            self.flat_grads.zero()
+        else:
+            self.optimizer.zero_grad(set_to_none=False)
         with torch.autocast(self.device.type, dtype=self.dtype, enabled=self.dtype != torch.float32):
             total, _ = self.module(dict(self.static_batch))
         total.backward()
+        return total.detach()
+
+    def _raw_opt(self):
         if self.grad_norm is not None:
             torch.nn.utils.clip_grad_norm_(self.parameters(), self.grad_norm, foreach=True)
         self.optimizer.step()
-        return total.detach()
+
+    def _raw_step(self):
+        loss = self._raw_fwd_bwd()
+        if self.flat_grads is not None:
+            self.flat_grads.all_reduce_mean()
+        self._raw_opt()
+        return loss
 
     def _advance_lr(self):
         self._sched_step += 1
@@ -122,6 +140,9 @@ class PretrainStep:
 
     def _capture(self, data_dict):
         self.static_batch = {k: v.clone() for k, v in data_dict.items() if torch.is_tensor(v)}
+        if self.dp_graph:
+            sync_module_state(self.module)
+            self.flat_grads = FlatGrads(self.parameters())
         cur = torch.cuda.current_stream(self.device)
         side = torch.cuda.Stream(self.device)
         side.wait_stream(cur)
@@ -134,8 +155,15 @@ class PretrainStep:
         from . import _lib
         n0 = _lib.launch_count()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.static_loss = self._raw_step()
+        if self.flat_grads is None:
+            with torch.cuda.graph(self.graph):
+                self.static_loss = self._raw_step()
+        else:
+            with torch.cuda.graph(self.graph):
+                self.static_loss = self._raw_fwd_bwd()
+            self.graph_opt = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_opt, pool=self.graph.pool()):
+                self._raw_opt()
         self.native_launches_per_step = _lib.launch_count() - n0   # native kernel nodes replayed per step
 
     def _graph_step(self, data_dict):
@@ -148,6 +176,9 @@ class PretrainStep:
             if src.data_ptr() != dst.data_ptr():
                 dst.copy_(src, non_blocking=True)
         self.graph.replay()
+        if self.flat_grads is not None:
+            self.flat_grads.all_reduce_mean()
+            self.graph_opt.replay()
         self._advance_lr()
         return self.static_loss
 
@@ -167,6 +198,38 @@ class PretrainStep:
         self.optimizer.step()
         self.scheduler.step()
         return total.detach()
+
+
+class FlatGrads:
+    """Gradients of `params` as views of ONE flat fp32 buffer, so that the data-parallel mean is a single NCCL call (the
+    reference's DDP reduces the same 491 MB in 25 MB buckets, trainer/build.py:66-75)."""
+
+    def __init__(self, params):
+        self.params = [p for p in params if p.requires_grad]
+        n = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(n, dtype=self.params[0].dtype, device=self.params[0].device)
+        o = 0
+        for p in self.params:
+            p.grad = self.flat[o:o + p.numel()].view_as(p)
+            o += p.numel()
+
+    def zero(self):
+        self.flat.zero_()
+
+    def all_reduce_mean(self, group=None):
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            if dist.get_backend(group) == "nccl":
+                dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=group)
+            else:
+                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+                self.flat.div_(dist.get_world_size(group))
+
+
+def sync_module_state(module, src=0):
+    """What DDP does at construction: every rank starts from rank `src`'s parameters and buffers."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        for t in list(module.parameters()) + list(module.buffers()):
+            dist.broadcast(t.data, src)
 
 
 def batch_to_device(np_batch, device, pinned=None, non_blocking=True):

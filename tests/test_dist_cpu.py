@@ -59,6 +59,25 @@ def _worker(rank, world, port, q):
         gathered = [torch.zeros_like(lin.weight.grad) for _ in range(world)]
         dist.all_gather(gathered, lin.weight.grad)
         assert torch.allclose(gathered[0], gathered[1])
+        # 4. the graph-mode data-parallel path: flat gradient buffer + one all-reduce (mean) == DDP's gradient mean
+        from sceneverse_b200 import train
+        lin2 = torch.nn.Linear(D, 3)
+        if rank == 1:
+            with torch.no_grad():
+                for p in lin2.parameters():
+                    p.add_(1.0)                       # deliberately out of sync: sync_module_state must repair it
+        train.sync_module_state(lin2)
+        with torch.no_grad():
+            for p2, p1 in zip(lin2.parameters(), lin.parameters()):
+                p2.copy_(p1)
+        fg = train.FlatGrads(list(lin2.parameters()))
+        for _ in range(2):                            # the second pass checks zero() + in-place accumulation into the views
+            fg.zero()
+            lin2(x).pow(2).sum().backward()
+            assert lin2.weight.grad.data_ptr() == fg.flat.data_ptr()
+            fg.all_reduce_mean()
+            assert torch.allclose(lin2.weight.grad, lin.weight.grad, atol=1e-6), (lin2.weight.grad, lin.weight.grad)
+            assert torch.allclose(lin2.bias.grad, lin.bias.grad, atol=1e-6)
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         q.put((rank, repr(e)))
