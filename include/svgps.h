@@ -113,6 +113,12 @@ int sv_layer_norm_scratch_floats(int D);
  * graph) and every replay draws fresh masks while forward and backward of the same step still agree.  NULL unregisters. */
 int sv_dropout_seed_offset(const unsigned long long *device_counter);
 
+/* Column sums out[c] = sum_r x[r][c] of a row-major (R, N) bf16 / f32 matrix (rows row_stride elements apart, N % 8 == 0),
+ * fp32 accumulation, deterministic: the bias gradient of a linear layer (reference: autograd of every nn.Linear of the
+ * stack, e.g. modules/layers/transformers.py:122-134).  scratch: sv_colsum_scratch_floats(N) floats. */
+int sv_colsum(const void *x, long long row_stride, int is_bf16, int R, int N, float *out, float *scratch, void *stream);
+int sv_colsum_scratch_floats(int N);
+
 /* calc_pairwise_locs, 'center' relation (reference: modules/utils.py:38-87): centers (B,O,*) f32 with row stride
  * row_stride (>= 3 floats; xyz first) -> out (B,O,O,5) f32 = [dist/max_dist, dz/dist, dist2d/dist, dy/dist2d, dx/dist2d];
  * dist_norm = 0 keeps the raw distance in slot 0.  eps sits inside the square roots (1e-10 in the reference). */

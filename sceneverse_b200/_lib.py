@@ -95,6 +95,8 @@ _GPS_SIGS = {
                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "sv_layer_norm_scratch_floats": [c_int],
     "sv_dropout_seed_offset": [c_void_p],
+    "sv_colsum": [c_void_p, ctypes.c_longlong, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
+    "sv_colsum_scratch_floats": [c_int],
     "sv_sa_mlp_param_bytes": [c_int],
     "sv_sa1_mlp_bf16": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
     "sv_sa2_mlp_bf16": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],

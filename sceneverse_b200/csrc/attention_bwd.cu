@@ -5,11 +5,12 @@
 // P is recomputed from Q, K, the gate and the saved log-sum-exp; the dropout mask is regenerated from (seed, indices);
 // no (B,H,L,T) tensor is ever stored.  Reference math: autograd of modules/layers/transformers.py:188-237 and of
 // nn.MultiheadAttention's core (transformers.py:22-24,69-74,118-120).
-// Structure (both sides): the "row" operand pair (Q,dO | K,V) is a 128-row TMA tile, the "column" operand pair
-// (K,V | Q,dO) is staged once per (scene, head); the columns are swept in blocks of 64: two tcgen05.mma chains fill
-// 2 x 64 TMEM columns, the element-wise stage (one thread per row, the two warpgroups split the block's 16-column
-// units) writes the bf16 dS / P tiles, and the output MMAs accumulate over the blocks reading the SAME staged column
-// operand MN-major.  TMEM: 4 x 64 columns, shared memory ~100 KB -> two CTAs per SM.
+// Structure (both sides): the "row" operand pair (Q,dO | K,V) is a 128-row TMA tile; the "column" operand pair
+// (K,V | Q,dO) is streamed in blocks of 64 rows through a two-deep TMA ring (the next block lands behind the current
+// element-wise stage).  Per block: two tcgen05.mma chains fill 2 x 64 TMEM columns, the element-wise stage (one thread
+// per row, the two warpgroups split the block's 16-column units) writes the bf16 dS / P tiles, and the output MMAs
+// accumulate over the blocks reading the SAME staged block MN-major.  TMEM: 4 x 64 columns, shared memory 80-110 KB
+// independent of the sequence length -> two CTAs per SM for every shape up to 384 x 384.
 #include "attn_common.cuh"
 #include "svgps.h"
 
@@ -71,9 +72,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mR1, const __grid_constant__
   const int NC = (Lc + 15) & ~15;
   uint8_t *sR1 = smem;                       // [128][64] sw128   Q  | K
   uint8_t *sR2 = sR1 + 16384;                // [128][64] sw128   dO | V
-  uint8_t *sC1 = sR2 + 16384;                // [NC][64]  sw128   K  | Q
-  uint8_t *sC2 = sC1 + NC * 128;             // [NC][64]  sw128   V  | dO
-  uint8_t *sG1 = sC2 + NC * 128;             // [8][128][8] K-major   scale * dS (^T)
+  uint8_t *sC = sR2 + 16384;                 // 2 buffers x { [64][64] sw128 K | Q block, [64][64] sw128 V | dO block }
+  uint8_t *sG1 = sC + 2 * 16384;             // [8][128][8] K-major   scale * dS (^T)
   uint8_t *sG2 = sG1 + 16384;                // [8][128][8] K-major   dropped P^T (SIDE 1)
   float *vec = reinterpret_cast<float *>(sG2 + (SIDE == 1 ? 16384 : 0));
   // SIDE 0: vec = kb[NC] | red[128][6] (GATED)      SIDE 1: vec = lse2[NC] | Dv[NC] | rk[NC] | W[NC][6] (GATED)
@@ -81,18 +81,28 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mR1, const __grid_constant__
   float *lse2s = vec, *Dv = vec + NC;
   uint32_t *rks = reinterpret_cast<uint32_t *>(vec + 2 * NC);
   float *Ws = vec + 3 * NC;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(vec + (SIDE == 0 ? NC + 768 : 9 * NC));  // 0: C landed, 1: R tile, 2: MMA
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3);
+  // barriers 0,1: column block landed in buffer 0 / 1, 2: row tile landed, 3: MMA done
+  uint64_t *bars = reinterpret_cast<uint64_t *>(vec + (SIDE == 0 ? NC + 768 : 9 * NC));
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wg = warp >> 2, wq = warp & 3;
   const int row = wq * 32 + lane;
   const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
   const int E = a.H * DH;
+  const int nblk = (NC + 63) >> 6;
+  // column block `cb` of a tile (rows [64 cb, 64 cb + nb) of the column operands) -> staging buffer `buf`
+  auto load_cblock = [&](int cb, int buf) {
+    const int nb = min(64, NC - cb * 64);
+    mbar_expect_tx(&bars[buf], 2 * rows_bytes(cb * 64, nb >> 4, Lc));
+    tma_rows(sC + buf * 16384, &mC1, h, cb * 64, nb >> 4, Lc, b, &bars[buf]);
+    tma_rows(sC + buf * 16384 + 8192, &mC2, h, cb * 64, nb >> 4, Lc, b, &bars[buf]);
+  };
 
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
     mbar_init(&bars[2], 1);
+    mbar_init(&bars[3], 1);
     mbar_fence_init();
     tma_prefetch_desc(&mR1);
     tma_prefetch_desc(&mR2);
@@ -101,12 +111,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mR1, const __grid_constant__
   }
   __syncthreads();
   if (tid == 0) {
-    mbar_expect_tx(&bars[0], 2 * rows_bytes(0, NC >> 4, Lc));
-    tma_rows(sC1, &mC1, h, 0, NC >> 4, Lc, b, &bars[0]);
-    tma_rows(sC2, &mC2, h, 0, NC >> 4, Lc, b, &bars[0]);
-    mbar_expect_tx(&bars[1], 2 * rows_bytes(0, 8, Lr));
-    tma_rows(sR1, &mR1, h, 0, 8, Lr, b, &bars[1]);
-    tma_rows(sR2, &mR2, h, 0, 8, Lr, b, &bars[1]);
+    load_cblock(0, 0);
+    mbar_expect_tx(&bars[2], 2 * rows_bytes(0, 8, Lr));
+    tma_rows(sR1, &mR1, h, 0, 8, Lr, b, &bars[2]);
+    tma_rows(sR2, &mR2, h, 0, 8, Lr, b, &bars[2]);
   }
   if (warp == 1) tmem_alloc_n(tmem_slot, TMEM_COLS);
   // per-column vectors
@@ -132,8 +140,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mR1, const __grid_constant__
   const uint32_t tmem = *tmem_slot;
   const uint32_t trow = tmem + ((uint32_t)(wq * 32) << 16);
   const float c2 = a.scale * LOG2E;
-  const int nblk = (NC + 63) >> 6;
   uint32_t ph_r = 0, ph_m = 0;
+  int cbi = 0;  // running column-block counter: buffer = cbi & 1, phase of its barrier = (cbi >> 1) & 1
 
   for (int r0 = 0; r0 < Lr; r0 += 128) {
     const int ri = r0 + row;                     // query (SIDE 0) / key (SIDE 1) of this thread
@@ -175,17 +183,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mR1, const __grid_constant__
     }
     const bool vec_loc = SIDE == 0 && GATED && (a.Lk & 3) == 0;
 
-    for (int blk = 0; blk < nblk; ++blk) {
+    for (int blk = 0; blk < nblk; ++blk, ++cbi) {
       const int nb = min(64, NC - blk * 64);     // columns of this block (multiple of 16)
+      const int buf = cbi & 1;
       // ---- S_blk, dP_blk ---------------------------------------------------------------------------------------------
       if (tid == 0) {
-        if (blk == 0) {
-          if (r0 == 0) mbar_wait(&bars[0], 0);
-          mbar_wait(&bars[1], ph_r);
-        }
+        if (blk == 0) mbar_wait(&bars[2], ph_r);
+        mbar_wait(&bars[buf], (uint32_t)(cbi >> 1) & 1u);
         fence_after_sync();
         const uint32_t aR1 = smem_u32(sR1), aR2 = smem_u32(sR2);
-        const uint32_t aC1 = smem_u32(sC1) + blk * 8192, aC2 = smem_u32(sC2) + blk * 8192;
+        const uint32_t aC1 = smem_u32(sC) + buf * 16384, aC2 = aC1 + 8192;
         const uint32_t idesc = idesc_kk(nb);
 #pragma unroll
         for (int ks = 0; ks < DH / 16; ++ks)
@@ -193,15 +200,21 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mR1, const __grid_constant__
 #pragma unroll
         for (int ks = 0; ks < DH / 16; ++ks)
           mma_bf16(tmem + COL_DP, make_desc_sw128(aR2 + ks * 32), make_desc_sw128(aC2 + ks * 32), idesc, ks > 0);
-        mma_commit(&bars[2]);
+        mma_commit(&bars[3]);
       }
-      mbar_wait(&bars[2], ph_m);
+      mbar_wait(&bars[3], ph_m);
       ph_m ^= 1u;
       fence_after_sync();
+      // every MMA issued before this commit has retired: the OTHER buffer (read last by the previous block's output MMAs) is
+      // free -> stream the next column block (of this row tile or the first of the next) behind the element-wise stage
+      if (tid == 0) {
+        if (blk + 1 < nblk) load_cblock(blk + 1, buf ^ 1);
+        else if (r0 + 128 < Lr) load_cblock(0, buf ^ 1);
+      }
       if (tid == 0 && blk == nblk - 1 && r0 + 128 < Lr) {  // row operands are free: fetch the next tile
-        mbar_expect_tx(&bars[1], 2 * rows_bytes(r0 + 128, 8, Lr));
-        tma_rows(sR1, &mR1, h, r0 + 128, 8, Lr, b, &bars[1]);
-        tma_rows(sR2, &mR2, h, r0 + 128, 8, Lr, b, &bars[1]);
+        mbar_expect_tx(&bars[2], 2 * rows_bytes(r0 + 128, 8, Lr));
+        tma_rows(sR1, &mR1, h, r0 + 128, 8, Lr, b, &bars[2]);
+        tma_rows(sR2, &mR2, h, r0 + 128, 8, Lr, b, &bars[2]);
       }
 
       // ---- element-wise stage: 16-column units, alternating between the warpgroups ----------------------------------------
@@ -213,35 +226,69 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mR1, const __grid_constant__
           uint32_t rs[16], rd[16];
           tmem_ld16_async(trow + COL_S + cl, rs);
           tmem_ld16_async(trow + COL_DP + cl, rd);
+          if (SIDE == 0 && GATED) {
+            // gated query-side unit: per group of 4 keys the 20 geometry floats are loaded ONCE and serve both the gate
+            // and the six gate-weight gradients
+            tmem_wait16(rs);
+            tmem_wait16(rd);
+            float ds[16];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int cq = c0 + q * 4;
+              float l[4][5];
+              bool have[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) have[e] = loc != nullptr && cq + e < a.Lk;
+              if (vec_loc) {
+                if (have[0]) {
+                  const float4 *l4 = reinterpret_cast<const float4 *>(loc + (size_t)cq * 5);
+                  const float4 A = __ldg(l4), B2 = __ldg(l4 + 1), C = __ldg(l4 + 2), Dd = __ldg(l4 + 3), Ee = __ldg(l4 + 4);
+                  l[0][0] = A.x; l[0][1] = A.y; l[0][2] = A.z; l[0][3] = A.w; l[0][4] = B2.x;
+                  l[1][0] = B2.y; l[1][1] = B2.z; l[1][2] = B2.w; l[1][3] = C.x; l[1][4] = C.y;
+                  l[2][0] = C.z; l[2][1] = C.w; l[2][2] = Dd.x; l[2][3] = Dd.y; l[2][4] = Dd.z;
+                  l[3][0] = Dd.w; l[3][1] = Ee.x; l[3][2] = Ee.y; l[3][3] = Ee.z; l[3][4] = Ee.w;
+                }
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  if (have[e]) {
+                    const float *lp = loc + (size_t)(cq + e) * 5;
+#pragma unroll
+                    for (int t = 0; t < 5; ++t) l[e][t] = __ldg(lp + t);
+                  }
+              }
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int i = q * 4 + e;
+                const float gli = have[e] ? gw.log2gate(l[e][0], l[e][1], l[e][2], l[e][3], l[e][4]) : 0.f;
+                const float p = ex2f(fmaf(u2f(rs[i]), c2, kb[c0 + i]) - lse2 + gli);
+                const float dsi = p * (u2f(rd[i]) - D);
+                if (have[e] && gli > LOG2_CLAMP) {                       // clamp(sigmoid, 1e-6) inactive
+                  const float dz = dsi * (1.0f - ex2f(gli));            // d log(sigmoid(z)) / dz = 1 - sigmoid(z)
+                  gb += dz;
+                  g0 = fmaf(dz, l[e][0], g0);
+                  g1 = fmaf(dz, l[e][1], g1);
+                  g2a = fmaf(dz, l[e][2], g2a);
+                  g3 = fmaf(dz, l[e][3], g3);
+                  g4 = fmaf(dz, l[e][4], g4);
+                }
+                ds[i] = dsi * a.scale;
+              }
+            }
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+              uint32_t w[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) w[e] = pack_bf16(ds[hf * 8 + e * 2], ds[hf * 8 + e * 2 + 1]);
+              *reinterpret_cast<uint4 *>(sG1 + tile_off(128, row, cl + hf * 8)) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+            continue;
+          }
           float gl[16];
           if (GATED) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) gl[i] = 0.f;
-            if (SIDE == 0) {
-              if (loc != nullptr) {
-                if (vec_loc) {
-                  const float4 *l4 = reinterpret_cast<const float4 *>(loc + (size_t)c0 * 5);
-#pragma unroll
-                  for (int q = 0; q < 4; ++q) {
-                    if (c0 + q * 4 < a.Lk) {
-                      const float4 A = __ldg(l4 + q * 5), B2 = __ldg(l4 + q * 5 + 1), C = __ldg(l4 + q * 5 + 2),
-                                   Dd = __ldg(l4 + q * 5 + 3), Ee = __ldg(l4 + q * 5 + 4);
-                      gl[q * 4] = gw.log2gate(A.x, A.y, A.z, A.w, B2.x);
-                      gl[q * 4 + 1] = gw.log2gate(B2.y, B2.z, B2.w, C.x, C.y);
-                      gl[q * 4 + 2] = gw.log2gate(C.z, C.w, Dd.x, Dd.y, Dd.z);
-                      gl[q * 4 + 3] = gw.log2gate(Dd.w, Ee.x, Ee.y, Ee.z, Ee.w);
-                    }
-                  }
-                } else {
-#pragma unroll
-                  for (int i = 0; i < 16; ++i)
-                    if (c0 + i < a.Lk) {
-                      const float *l = loc + (size_t)(c0 + i) * 5;
-                      gl[i] = gw.log2gate(l[0], l[1], l[2], l[3], l[4]);
-                    }
-                }
-              }
-            } else if (klive) {
+            if (SIDE == 1 && klive) {
 #pragma unroll
               for (int i = 0; i < 16; ++i)
                 if (c0 + i < a.Lq) {
@@ -275,18 +322,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mR1, const __grid_constant__
               dpi *= m;
             }
             const float dsi = p * (dpi - (SIDE == 0 ? D : Dv[c0 + i]));
-            if (SIDE == 0 && GATED) {
-              if (gl[i] > LOG2_CLAMP && c0 + i < a.Lk && loc != nullptr) {  // clamp(sigmoid, 1e-6) inactive
-                const float dz = dsi * (1.0f - ex2f(gl[i]));                // d log(sigmoid(z)) / dz = 1 - sigmoid(z)
-                const float *l = loc + (size_t)(c0 + i) * 5;
-                gb += dz;
-                g0 = fmaf(dz, __ldg(l), g0);
-                g1 = fmaf(dz, __ldg(l + 1), g1);
-                g2a = fmaf(dz, __ldg(l + 2), g2a);
-                g3 = fmaf(dz, __ldg(l + 3), g3);
-                g4 = fmaf(dz, __ldg(l + 4), g4);
-              }
-            }
             ds[i] = dsi * a.scale;
             pd[i] = p * m;
           }
@@ -316,7 +351,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mR1, const __grid_constant__
       if (tid == 0) {
         fence_after_sync();
         const uint32_t aG1 = smem_u32(sG1), aG2 = smem_u32(sG2);
-        const uint32_t aC1 = smem_u32(sC1) + blk * 8192, aC2 = smem_u32(sC2) + blk * 8192;
+        const uint32_t aC1 = smem_u32(sC) + buf * 16384, aC2 = aC1 + 8192;
         const uint32_t idesc = idesc_kmn(DH);
 #pragma unroll 1
         for (int ks = 0; ks < (nb >> 4); ++ks) {
@@ -326,10 +361,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mR1, const __grid_constant__
             mma_bf16(tmem + COL_O2, make_desc(aG2 + ks * 4096, 2048, 128), make_desc_sw128_mn(aC2 + ks * 2048), idesc,
                      (blk | ks) != 0);
         }
-        if (blk == nblk - 1) mma_commit(&bars[2]);
+        if (blk == nblk - 1) mma_commit(&bars[3]);
       }
     }
-    mbar_wait(&bars[2], ph_m);
+    mbar_wait(&bars[3], ph_m);
     ph_m ^= 1u;
     fence_after_sync();
     ph_r ^= 1u;
@@ -384,9 +419,8 @@ int launch_side(const CUtensorMap &r1, const CUtensorMap &r2, const CUtensorMap 
                 const BwdArgs &a, cudaStream_t st) {
   const int Lc = SIDE == 0 ? a.Lk : a.Lq;
   const int NC = (Lc + 15) & ~15;
-  const size_t smem = 32768 + (size_t)NC * 256 + (SIDE == 1 ? 32768 : 16384) +
-                      (size_t)(SIDE == 0 ? NC + 768 : 9 * NC) * 4 + 64;
-  constexpr size_t SMEM_MAX = 32768 + 384 * 256 + 32768 + 9 * 384 * 4 + 64;
+  const size_t smem = 32768 + 32768 + (SIDE == 1 ? 32768 : 16384) + (size_t)(SIDE == 0 ? NC + 768 : 9 * NC) * 4 + 64;
+  constexpr size_t SMEM_MAX = 32768 + 32768 + 32768 + 9 * 384 * 4 + 64;
   auto kern = attn_bwd_kernel<SIDE, GATED, DROP>;
   static bool configured[64] = {false};
   int dev = 0;

@@ -103,6 +103,8 @@ class OpenVocab(nn.Module):
         for head in self.head_list:
             setattr(self, head, build_module("heads", getattr(cfg.model.heads, head)))
         self.use_scene_cap = cfg.data.args.get("use_scene_cap", False)
+        from .modules.layers import route_linears
+        route_linears(self)
 
     def forward(self, data_dict):
         if 'cur_step' not in data_dict:

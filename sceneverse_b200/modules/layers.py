@@ -22,6 +22,21 @@ def get_activation_fn(activation_type):
     return getattr(F, activation_type)
 
 
+class Linear(nn.Linear):
+    """nn.Linear (same parameters / state_dict) routed through ops.linear (native bias gradient, fp32 weight gradient)."""
+
+    def forward(self, x):
+        return ops.linear(x, self.weight, self.bias)
+
+
+def route_linears(module):
+    """Re-class every plain nn.Linear below `module` (incl. third-party sub-modules such as the HF BERT blocks)."""
+    for m in module.modules():
+        if type(m) is nn.Linear:
+            m.__class__ = Linear
+    return module
+
+
 class LayerNorm(nn.LayerNorm):
     """nn.LayerNorm (same parameters / state_dict) whose forward is the fused native dropout + residual + LayerNorm:
     norm(x, residual=r, dropout_p=p) == LayerNorm(r + dropout(x))."""

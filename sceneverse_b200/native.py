@@ -85,3 +85,17 @@ def attention_backward(q, k, v, out, grad_out, lse, num_heads, key_padding_mask=
             torch.cuda.current_stream(dev).cuda_stream)
     _lib.check(lib, st, "sv_attention_bwd_dropout_bf16")
     return dq, dk, dv, dsw
+
+
+def colsum(x):
+    """Column sums of a (R, N) bf16 / f32 matrix (rows may be strided) -> (N,) f32; deterministic native kernel."""
+    assert x.is_cuda and x.dim() == 2 and x.stride(1) == 1 and x.dtype in (torch.bfloat16, torch.float32)
+    R, N = x.shape
+    lib = _lib.gps()
+    out = torch.empty(N, dtype=torch.float32, device=x.device)
+    scratch = torch.empty(lib.sv_colsum_scratch_floats(N), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        st = lib.sv_colsum(x.data_ptr(), x.stride(0), 1 if x.dtype == torch.bfloat16 else 0, R, N, out.data_ptr(),
+                           scratch.data_ptr(), torch.cuda.current_stream(x.device).cuda_stream)
+    _lib.check(lib, st, "sv_colsum")
+    return out

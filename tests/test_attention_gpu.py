@@ -290,3 +290,41 @@ def test_dropout_seed_offset_counter_changes_masks():
         lib.sv_dropout_seed_offset(None)
     d = native.attention(q, k, v, H, dropout_p=0.2, seed=77)
     assert torch.equal(a, d)                                               # counter 0 == no counter
+
+
+@pytest.mark.parametrize("R,N,dtype", [(19200, 768, torch.bfloat16), (3200, 3072, torch.bfloat16), (77, 8, torch.float32),
+                                       (5000, 30528, torch.bfloat16), (1, 64, torch.bfloat16)])
+def test_colsum_kernel(R, N, dtype):
+    from sceneverse_b200 import native
+    x = rand(R, N, seed=R + N).to(dtype)
+    got = native.colsum(x)
+    want = x.double().sum(0)
+    assert got.dtype == torch.float32
+    assert (got.double() - want).abs().max().item() <= 1e-5 * max(1.0, x.double().abs().sum(0).max().item())
+    assert torch.equal(got, native.colsum(x))                       # deterministic
+    if N >= 16:                                                       # strided rows (a column slice of a wider matrix)
+        assert torch.allclose(native.colsum(x[:, : N // 2]), got[: N // 2], rtol=1e-6, atol=1e-6)
+
+
+def test_linear_fn_matches_autocast_linear():
+    """ops.linear's training path (library GEMMs + native bias gradient + fp32 weight gradient) vs F.linear under autocast."""
+    from sceneverse_b200 import ops
+    import torch.nn.functional as F
+    x = rand(4, 130, 768, seed=1).requires_grad_(True)
+    W = (rand(2048, 768, seed=2) * 0.05).requires_grad_(True)
+    b = (rand(2048, seed=3) * 0.1).requires_grad_(True)
+    go = rand(4, 130, 2048, seed=4)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y = ops.linear(x, W, b, activation="relu")
+    assert isinstance(y.grad_fn.next_functions[0][0], ops._LinearFn._backward_cls) or "Relu" in type(y.grad_fn).__name__
+    y.backward(go.bfloat16())
+    got = [y.detach().float(), x.grad.clone(), W.grad.clone(), b.grad.clone()]
+    assert W.grad.dtype == torch.float32 and b.grad.dtype == torch.float32 and x.grad.dtype == torch.float32
+    for t in (x, W, b):
+        t.grad = None
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        yr = F.relu(F.linear(x, W, b))
+    yr.backward(go.bfloat16())
+    for g, w, name in zip(got, (yr.detach().float(), x.grad, W.grad, b.grad), "yxWb"):
+        err = (g - w).abs().max().item() / (w.abs().max().item() + 1e-9)
+        assert err < 1e-2, (name, err)
