@@ -91,15 +91,6 @@ template <typename T, int MAXCH, bool HAS_RES, bool DROP>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const LnArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nch = a.D >> 3;
-  float gam[MAXCH][8], bet[MAXCH][8];
-#pragma unroll
-  for (int ch = 0; ch < MAXCH; ++ch) {
-    const int c = lane + 32 * ch;
-    if (c < nch) {
-      Chunk<float>::load(a.gamma, c, gam[ch]);
-      Chunk<float>::load(a.beta, c, bet[ch]);
-    }
-  }
   const float invD = 1.0f / (float)a.D;
   for (int row = blockIdx.x * 8 + warp; row < a.R; row += gridDim.x * 8) {
     const size_t base8 = (size_t)row * nch;
@@ -151,9 +142,11 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const LnArgs a) {
     for (int ch = 0; ch < MAXCH; ++ch) {
       const int c = lane + 32 * ch;
       if (c < nch) {
-        float o[8];
+        float o[8], gam[8], bet[8];  // gamma / beta come from L1 per row: keeping them resident costs 48 registers
+        Chunk<float>::load(a.gamma, c, gam);
+        Chunk<float>::load(a.beta, c, bet);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = fmaf((v[ch][i] - mean) * rstd, gam[ch][i], bet[ch][i]);
+        for (int i = 0; i < 8; ++i) o[i] = fmaf((v[ch][i] - mean) * rstd, gam[i], bet[i]);
         Chunk<T>::store(a.y, base8 + c, o);
       }
     }

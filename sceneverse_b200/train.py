@@ -122,7 +122,10 @@ class PretrainStep:
 
     def _raw_opt(self):
         if self.grad_norm is not None:
-            torch.nn.utils.clip_grad_norm_(self.parameters(), self.grad_norm, foreach=True)
+            if self.flat_grads is not None:
+                self.flat_grads.clip_norm_(self.grad_norm)     # same math as clip_grad_norm_, two kernels on the flat buffer
+            else:
+                torch.nn.utils.clip_grad_norm_(self.parameters(), self.grad_norm, foreach=True)
         self.optimizer.step()
 
     def _raw_step(self):
@@ -142,7 +145,7 @@ class PretrainStep:
         self.static_batch = {k: v.clone() for k, v in data_dict.items() if torch.is_tensor(v)}
         if self.dp_graph:
             sync_module_state(self.module)
-            self.flat_grads = FlatGrads(self.parameters())
+        self.flat_grads = FlatGrads(self.parameters())
         cur = torch.cuda.current_stream(self.device)
         side = torch.cuda.Stream(self.device)
         side.wait_stream(cur)
@@ -155,7 +158,7 @@ class PretrainStep:
         from . import _lib
         n0 = _lib.launch_count()
         self.graph = torch.cuda.CUDAGraph()
-        if self.flat_grads is None:
+        if not self.dp_graph:
             with torch.cuda.graph(self.graph):
                 self.static_loss = self._raw_step()
         else:
@@ -176,7 +179,7 @@ class PretrainStep:
             if src.data_ptr() != dst.data_ptr():
                 dst.copy_(src, non_blocking=True)
         self.graph.replay()
-        if self.flat_grads is not None:
+        if self.dp_graph:
             self.flat_grads.all_reduce_mean()
             self.graph_opt.replay()
         self._advance_lr()
@@ -215,6 +218,13 @@ class FlatGrads:
 
     def zero(self):
         self.flat.zero_()
+
+    def clip_norm_(self, max_norm, eps=1e-6):
+        """torch.nn.utils.clip_grad_norm_ (L2) on the flat buffer: the norm of the per-tensor norms is the norm of the
+        concatenation."""
+        total = torch.linalg.vector_norm(self.flat, 2.0)
+        self.flat.mul_((max_norm / (total + eps)).clamp(max=1.0))
+        return total
 
     def all_reduce_mean(self, group=None):
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
