@@ -169,9 +169,22 @@ class PretrainStep:
                 self._raw_opt()
         self.native_launches_per_step = _lib.launch_count() - n0   # native kernel nodes replayed per step
 
+    def _dp_graph_possible(self):
+        """Graph A must not contain an NCCL collective: with several ranks the contrastive exchange has to be the native
+        peer-memory kernel.  If symmetric memory could not be set up (losses then use NCCL all_gather), run eager DDP."""
+        from . import fused_gather
+        return all(v is not None for v in fused_gather._state.values())
+
     def _graph_step(self, data_dict):
         if not self.probed:
             self._probe_unused(data_dict)
+            if self.dp_graph and not self._dp_graph_possible():
+                self.graph_mode = self.dp_graph = False
+                self.use_ddp = True
+                self.ddp = nn.parallel.DistributedDataParallel(
+                    self.module, device_ids=[self.device.index], find_unused_parameters=False,
+                    gradient_as_bucket_view=True, bucket_cap_mb=64)
+                return self.step(data_dict)
         if self.graph is None:
             self._capture(data_dict)
         for k, dst in self.static_batch.items():
@@ -199,7 +212,10 @@ class PretrainStep:
         if self.grad_norm is not None:
             torch.nn.utils.clip_grad_norm_(self.parameters(), self.grad_norm, foreach=True)
         self.optimizer.step()
-        self.scheduler.step()
+        if self.scheduler is not None:
+            self.scheduler.step()
+        else:                       # capturable optimizer (graph mode was requested but is not possible): tensor lr
+            self._advance_lr()
         return total.detach()
 
 
