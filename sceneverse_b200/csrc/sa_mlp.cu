@@ -17,7 +17,9 @@
 // max can be taken on raw accumulators (affine + ReLU once per centre at the end).
 // CTA = NCG warpgroups of 128 threads (SA1: 2, two CTAs per SM; SA2: 4, one CTA per SM): every warpgroup covers the 128 TMEM lanes (rows) and owns 1/NCG of the
 // COLUMNS of every epilogue, so 16 warps per CTA hide the TMEM-load / shared-memory latencies of the short epilogue
-// phases.  Thread 0 issues the MMAs; completion comes back through an mbarrier.
+// phases.  One EXTRA warp is the MMA issuer: the epilogue threads never meet in a CTA-wide barrier — each arrives on the
+// tile's `a_ready` mbarrier when its part of the next A operand is in shared memory and moves straight on to the other
+// tile in flight; the issuer waits for `a_ready`, issues the layer's MMAs and commits to `mma_done`.
 #include <cuda_bf16.h>
 
 #include "svcommon.h"
@@ -31,7 +33,11 @@ using namespace tc05;
 template <int KF_, int K1P_, int N1_, int N2_, int N3_, int CPC_, int NCG_>
 struct SaCfg {
   static constexpr int NCG = NCG_;  // column groups (warpgroups of 128 threads) per CTA
-  static constexpr int NTHREADS = 128 * NCG_;
+  static constexpr int NTHREADS = 128 * NCG_;         // epilogue / gather threads
+  // SA2 (tensor-pipe bound, one CTA per SM) gets a dedicated MMA issuer warp; SA1 (CUDA-core bound, two CTAs per SM,
+  // measured slower with the extra warp's register cost) keeps a CTA barrier + thread 0 as the issuer
+  static constexpr bool ISSUER = NCG_ == 4;
+  static constexpr int NTHREADS_ALL = 128 * NCG_ + (ISSUER ? 32 : 0);
   static constexpr int KF = KF_;    // feature channels gathered per neighbour (3 = rgb, 128 = SA1 output)
   static constexpr int K1P = K1P_;  // layer-1 K (3 + KF) padded to a multiple of 16
   static constexpr int N1 = N1_, N2 = N2_, N3 = N3_;
@@ -104,7 +110,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // A buffer, TMEM column range and mbarrier, so the tensor pipe works on one while the CUDA cores run the
 // epilogue / gather of the other.
 template <class Cfg, int LEVEL>
-__global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::NCG == 2 ? 2 : 1) sa_mlp_kernel(const SaMlpArgs a) {
+__global__ void __launch_bounds__(Cfg::NTHREADS_ALL, Cfg::NCG == 2 ? 2 : 1) sa_mlp_kernel(const SaMlpArgs a) {
   constexpr int NCG = Cfg::NCG, NTHREADS = Cfg::NTHREADS;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t *sW1 = smem + 2 * Cfg::A_BYTES;
@@ -114,23 +120,28 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::NCG == 2 ? 2 : 1) sa_mlp_k
   const float *sh2 = sh1 + Cfg::N1;
   const float *sh3 = sh2 + Cfg::N2;
   uint64_t *wbar = reinterpret_cast<uint64_t *>(smem + 2 * Cfg::A_BYTES + Cfg::PARAM_BYTES);
-  uint64_t *mbar = wbar + 1;  // [2]
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(mbar + 2);
+  uint64_t *mbar = wbar + 1;    // [2] mma_done: the issuer's tcgen05.commit of the tile in buffer b
+  uint64_t *abar = mbar + 2;    // [2] a_ready: every epilogue thread has written its part of buffer b's next A operand
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(abar + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, wg = tid >> 7;  // wg = column group of this thread
   const int r = tid & 127;  // row of the tile == TMEM lane == centre within the super-tile
+  const bool is_issuer = Cfg::ISSUER && warp == 4 * NCG;  // the extra warp
+  const bool tmem_owner = Cfg::ISSUER ? is_issuer : warp == 1;
 
   if (tid == 0) {
     mbar_init(wbar, 1);
     mbar_init(mbar, 1);
     mbar_init(mbar + 1, 1);
+    mbar_init(abar, NTHREADS);
+    mbar_init(abar + 1, NTHREADS);
     mbar_fence_init();
     mbar_expect_tx(wbar, Cfg::PARAM_BYTES);
     bulk_g2s(sW1, a.params, Cfg::PARAM_BYTES, wbar);
   }
-  if (warp == 1) tmem_alloc<2 * Cfg::TMEM_COLS>(tmem_slot);
+  if (tmem_owner) tmem_alloc<2 * Cfg::TMEM_COLS>(tmem_slot);
   // zero both A tiles once: K-padding columns that no gather / epilogue writes stay zero for the whole kernel
-  for (int e = tid; e < 2 * Cfg::A_BYTES / 16; e += NTHREADS) reinterpret_cast<uint4 *>(smem)[e] = make_uint4(0, 0, 0, 0);
+  for (int e = tid; e < 2 * Cfg::A_BYTES / 16; e += Cfg::NTHREADS_ALL) reinterpret_cast<uint4 *>(smem)[e] = make_uint4(0, 0, 0, 0);
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -143,7 +154,7 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::NCG == 2 ? 2 : 1) sa_mlp_k
   const uint32_t aW1 = smem_u32(sW1), aW2 = smem_u32(sW2), aW3 = smem_u32(sW3);
   uint32_t phase[2] = {0u, 0u};
 
-  // issue layer L (1..3) of buffer b; thread 0 only, after a __syncthreads
+  // issue layer L (1..3) of buffer b; issuer lane only, after a_ready[b]
   auto issue = [&](int L, int b) {
     fence_after_sync();
     const uint32_t aA = smem_u32(smem + b * Cfg::A_BYTES);
@@ -177,18 +188,49 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::NCG == 2 ? 2 : 1) sa_mlp_k
     phase[b] ^= 1u;
     fence_after_sync();
   };
-  // all threads: make this thread's smem writes visible to the tensor core, then let thread 0 issue
-  auto publish_and_issue = [&](int L, int b) {
+  // epilogue thread: its smem writes (generic proxy) and TMEM reads of buffer b are done -> arrive on a_ready[b]
+  // (without the issuer warp: CTA barrier, then thread 0 issues layer L itself)
+  auto publish = [&](int L, int b) {
     fence_proxy_async_smem();
     fence_before_sync();
-    __syncthreads();
-    if (tid == 0) issue(L, b);
+    if constexpr (Cfg::ISSUER) {
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(abar + b)) : "memory");
+    } else {
+      __syncthreads();
+      if (tid == 0) issue(L, b);
+    }
+  };
+  uint32_t aphase[2] = {0u, 0u};
+  // issuer lane: wait until every epilogue thread arrived for buffer b, then issue layer L
+  auto wait_and_issue = [&](int L, int b) {
+    mbar_wait(abar + b, aphase[b]);
+    aphase[b] ^= 1u;
+    issue(L, b);
   };
 
   const int n_centres = a.B * Cfg::CPC;
   const int n_super = (n_centres + 127) / 128;
   const int NS = a.NS;
   for (int st = blockIdx.x; st < n_super; st += gridDim.x) {
+    if (is_issuer) {
+      // same event order as the epilogue threads' program order: (L1,b0) (L1,b1) | per pair: (L2,b0) (L2,b1) (L3,b0)
+      // (L3,b1) (L1',b0) (L1',b1)
+      if ((tid & 31) == 0) {
+        wait_and_issue(1, 0);
+        if (1 < NS) wait_and_issue(1, 1);
+        for (int s = 0; s < NS; s += 2) {
+          const bool has1 = s + 1 < NS;
+#pragma unroll
+          for (int L = 1; L <= 2; ++L) {
+            wait_and_issue(L + 1, 0);
+            if (has1) wait_and_issue(L + 1, 1);
+          }
+          if (s + 2 < NS) wait_and_issue(1, 0);
+          if (has1 && s + 3 < NS) wait_and_issue(1, 1);
+        }
+      }
+      continue;
+    }
     const int cg = st * 128 + r;  // global centre index
     const bool live = cg < n_centres;
     const int cloud = live ? cg / Cfg::CPC : 0;
@@ -198,9 +240,19 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::NCG == 2 ? 2 : 1) sa_mlp_k
       cx = c[0]; cy = c[1]; cz = c[2];
     }
     const int *my_idx = a.ball_idx + (size_t)cg * NS;
-    float runmax[Cfg::N3 / NCG];
+    // running neighbourhood maximum of the raw layer-3 accumulators, kept as packed bf16 pairs: rounding is monotone, so
+    // max(round(x)) == round(max(x)) — half the registers of an fp32 running max (they pay for the issuer warp)
+    // (only where the issuer warp squeezes the register budget; SA1 keeps an fp32 running max)
+    constexpr bool PACKED = Cfg::ISSUER;
+    __nv_bfloat162 runmax[PACKED ? Cfg::N3 / NCG / 2 : 1];
+    float runmaxf[PACKED ? 1 : Cfg::N3 / NCG];
+    if constexpr (PACKED) {
 #pragma unroll
-    for (int i = 0; i < Cfg::N3 / NCG; ++i) runmax[i] = -INFINITY;
+      for (int i = 0; i < Cfg::N3 / NCG / 2; ++i) runmax[i] = __floats2bfloat162_rn(-INFINITY, -INFINITY);
+    } else {
+#pragma unroll
+      for (int i = 0; i < Cfg::N3 / NCG; ++i) runmaxf[i] = -INFINITY;
+    }
 
     // ---- gather of row r = (centre cg, sample s) into A buffer b, split in "load" (early) and "store" -----
     struct Pre { int k; float v0, v1, v2, v3, v4, v5; };
@@ -273,8 +325,14 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::NCG == 2 ? 2 : 1) sa_mlp_k
       for (int cc = 0; cc < Cfg::N3 / (32 * NCG); ++cc) {
         float v[32];
         tmem_ld32(tb + cc * 32, v);
+        if constexpr (PACKED) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) runmax[cc * 32 + i] = fmaxf(runmax[cc * 32 + i], v[i]);
+          for (int i = 0; i < 16; ++i)
+            runmax[cc * 16 + i] = __hmax2(runmax[cc * 16 + i], __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) runmaxf[cc * 32 + i] = fmaxf(runmaxf[cc * 32 + i], v[i]);
+        }
       }
     };
 
@@ -284,13 +342,8 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::NCG == 2 ? 2 : 1) sa_mlp_k
       gather_begin(0, p0);
       if (1 < NS) gather_begin(1, p1);
       gather_end();
-      fence_proxy_async_smem();
-      fence_before_sync();
-      __syncthreads();
-      if (tid == 0) {
-        issue(1, 0);
-        if (1 < NS) issue(1, 1);
-      }
+      publish(1, 0);
+      if (1 < NS) publish(1, 1);
     }
     for (int s = 0; s < NS; s += 2) {
       const bool has1 = s + 1 < NS;
@@ -299,11 +352,11 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::NCG == 2 ? 2 : 1) sa_mlp_k
       for (int L = 1; L <= 2; ++L) {
         wait_mma(0);
         epi12(L, 0);
-        publish_and_issue(L + 1, 0);
+        publish(L + 1, 0);
         if (has1) {
           wait_mma(1);
           epi12(L, 1);
-          publish_and_issue(L + 1, 1);
+          publish(L + 1, 1);
         }
       }
       // layer 3 done: A buffer free -> start the next gather, take the running max, hand the next tile to the tensor pipe
@@ -312,7 +365,7 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::NCG == 2 ? 2 : 1) sa_mlp_k
       epi3(0);
       if (s + 2 < NS) {
         gather_end();
-        publish_and_issue(1, 0);
+        publish(1, 0);
       }
       if (has1) {
         wait_mma(1);
@@ -320,7 +373,7 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::NCG == 2 ? 2 : 1) sa_mlp_k
         epi3(1);
         if (s + 3 < NS) {
           gather_end();
-          publish_and_issue(1, 1);
+          publish(1, 1);
         }
       }
     }
@@ -335,22 +388,24 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::NCG == 2 ? 2 : 1) sa_mlp_k
         for (int h = 0; h < 4; ++h) {
           const int c = q * 8 + h * 2;
           const int gc = wg * (Cfg::N3 / NCG) + c;
-          w[h] = pack_bf16(fmaxf(runmax[c] + sh3[gc], 0.f), fmaxf(runmax[c + 1] + sh3[gc + 1], 0.f));
+          float2 m;
+          if constexpr (PACKED) m = __bfloat1622float2(runmax[c >> 1]);
+          else m = make_float2(runmaxf[c], runmaxf[c + 1]);
+          w[h] = pack_bf16(fmaxf(m.x + sh3[gc], 0.f), fmaxf(m.y + sh3[gc + 1], 0.f));
         }
         o[q] = make_uint4(w[0], w[1], w[2], w[3]);
       }
     }
-    // the next super-tile's first MMA overwrites TMEM that this one's last epilogue read
-    fence_before_sync();
-    __syncthreads();
+    // the next super-tile's first MMA overwrites TMEM that this one's last epilogue read: ordered by the a_ready arrival
+    // of the next prologue (publish() carries the tcgen05 fence) / by the CTA barrier of the next prologue
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<2 * Cfg::TMEM_COLS>(tmem);
+  if (tmem_owner) tmem_dealloc<2 * Cfg::TMEM_COLS>(tmem);
 }
 
-using Sa1 = SaCfg<3, 16, 64, 64, 128, 32, 2>;   // 256 threads, 2 CTAs / SM
-using Sa2 = SaCfg<128, 144, 128, 128, 256, 16, 4>;  // 512 threads, 1 CTA / SM
+using Sa1 = SaCfg<3, 16, 64, 64, 128, 32, 2>;   // 256 + 32 threads, 2 CTAs / SM
+using Sa2 = SaCfg<128, 144, 128, 128, 256, 16, 4>;  // 512 + 32 threads, 1 CTA / SM
 
 template <class Cfg, int LEVEL>
 int launch_sa(const SaMlpArgs &a, cudaStream_t st) {
@@ -361,14 +416,14 @@ int launch_sa(const SaMlpArgs &a, cudaStream_t st) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-  rc = sv::cuda_status(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, Cfg::NTHREADS, Cfg::SMEM_BYTES));
+  rc = sv::cuda_status(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, Cfg::NTHREADS_ALL, Cfg::SMEM_BYTES));
   if (rc) return rc;
   if (per_sm < 1) per_sm = 1;
   if (per_sm * 2 * Cfg::TMEM_COLS > 512) per_sm = 512 / (2 * Cfg::TMEM_COLS);  // TMEM columns are not part of the occupancy query
   const int n_super = (a.B * Cfg::CPC + 127) / 128;
   int grid = sms * per_sm;
   if (grid > n_super) grid = n_super;
-  kern<<<grid, Cfg::NTHREADS, Cfg::SMEM_BYTES, st>>>(a);
+  kern<<<grid, Cfg::NTHREADS_ALL, Cfg::SMEM_BYTES, st>>>(a);
   return sv::after_launch();
 }
 
