@@ -90,6 +90,40 @@ def _mm_f32(a, b):
     return torch.mm(a, b).float()
 
 
+# bf16 shadows of fp32 parameters, refreshed once per step with ONE multi-tensor copy (train.PretrainStep) instead of one
+# cast kernel per weight and per bias inside every linear (autocast's behaviour: ~200 tiny launches per step)
+_SHADOW = {}
+_SHADOW_LISTS = [[], []]   # (bf16 destinations, fp32 sources)
+
+
+def register_shadows(module):
+    """Create a bf16 shadow for every floating-point parameter of `module` that the bf16 linears read."""
+    for p in module.parameters():
+        if p.is_cuda and p.dtype == torch.float32 and p.dim() >= 1 and id(p) not in _SHADOW:
+            s = torch.empty_like(p, dtype=torch.bfloat16)
+            _SHADOW[id(p)] = (s, p)        # the strong reference to p keeps its id from being reused
+            _SHADOW_LISTS[0].append(s)
+            _SHADOW_LISTS[1].append(p.detach())
+    refresh_shadows()
+
+
+def refresh_shadows():
+    """Must run after every parameter update and before the next forward that should use the shadows."""
+    if _SHADOW_LISTS[0]:
+        torch._foreach_copy_(_SHADOW_LISTS[0], _SHADOW_LISTS[1])
+
+
+def clear_shadows():
+    _SHADOW.clear()
+    _SHADOW_LISTS[0].clear()
+    _SHADOW_LISTS[1].clear()
+
+
+def _bf16_of(p):
+    e = _SHADOW.get(id(p))
+    return e[0] if e is not None and e[1] is p else p.to(torch.bfloat16)
+
+
 class _LinearFn(torch.autograd.Function):
     """Training-path linear in bf16: y = x W^T + b.  The three GEMMs are plain library GEMMs (cuBLAS, the weight is cast
     to bf16 once per call exactly as autocast would); the bias gradient — a strided ATen reduction in the reference's
@@ -98,13 +132,13 @@ class _LinearFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias):
-        wb = weight.to(torch.bfloat16)
+        wb = _bf16_of(weight)
         x2 = x.reshape(-1, x.shape[-1])
         if x2.dtype != torch.bfloat16:
             x2 = x2.to(torch.bfloat16)
         ctx.save_for_backward(x2, wb)
         ctx.in_shape, ctx.in_dtype = x.shape, x.dtype
-        y = F.linear(x2, wb, bias.to(torch.bfloat16) if bias is not None else None)
+        y = F.linear(x2, wb, _bf16_of(bias) if bias is not None else None)
         return y.view(*x.shape[:-1], -1)
 
     @staticmethod

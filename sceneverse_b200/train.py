@@ -11,6 +11,7 @@ import torch.distributed as dist
 from torch import nn
 
 from . import model as M
+from . import ops
 from .modules import losses as L
 
 # parameters of the reference model that are constructed but never used in OpenVocab.forward
@@ -111,6 +112,7 @@ class PretrainStep:
     # ---- CUDA-graph path ---------------------------------------------------------------------------------------------
     def _raw_fwd_bwd(self):
         self._step_counter.add_(1)
+        ops.refresh_shadows()      # one multi-tensor fp32 -> bf16 copy of all weights (instead of a cast per linear)
         if self.flat_grads is not None:
             self.flat_grads.zero()
         else:
@@ -143,6 +145,9 @@ class PretrainStep:
 
     def _capture(self, data_dict):
         self.static_batch = {k: v.clone() for k, v in data_dict.items() if torch.is_tensor(v)}
+        if self.dtype == torch.bfloat16:
+            ops.clear_shadows()
+            ops.register_shadows(self.module)
         if self.dp_graph:
             sync_module_state(self.module)
         self.flat_grads = FlatGrads(self.parameters())

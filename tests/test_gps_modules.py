@@ -191,3 +191,6 @@ def test_training_step_cuda_graph_replay():
     assert np.isfinite(l_other) and abs(l_other - seen[-1]) > 1e-6       # a different batch went through the graph
     assert float(ps.optimizer.param_groups[0]["lr"]) != lr0 or ps._sched_step > 0
     _lib.gps().sv_dropout_seed_offset(None)                               # do not leak the counter into later tests
+    from sceneverse_b200 import ops
+    assert len(ops._SHADOW) > 100                                         # bf16 weight shadows were in use
+    ops.clear_shadows()
