@@ -44,6 +44,14 @@ int sv_sa2_mlp_bf16(const float *xyz, const void *feat, const float *new_xyz, co
  * rowmax = 16: instead store max over each group of 16 consecutive rows into out[M/16,N] (PointNet++ SA3 max-pool). */
 int sv_gemm_bf16(const void *A, int lda, const void *B, int ldb, int M, int N, int K, const float *bias, int act,
                  const void *residual, void *out, int ldo, int out_f32, int rowmax, void *stream);
+/* Same GEMM with either operand given TRANSPOSED in memory (the two backward GEMMs of a linear layer without any copy):
+ * a_transposed = 1: A is stored (K, M) row-major, lda >= M;  b_transposed = 1: B is stored (K, N) row-major, ldb >= N.
+ * The staged tiles are then read by the tensor core as MN-major operands.  dgrad of y = x W^T: dx = g . W  ->
+ * sv_gemm_bf16_ex(g, N, 0, W, Kin, 1, M, Kin, N, ...);  wgrad: dW = g^T . x -> sv_gemm_bf16_ex(g, N, 1, x, Kin, 1, N, Kin, M,
+ * ..., out_f32 = 1).  (reference: autograd of every nn.Linear of the stack, e.g. modules/layers/transformers.py:122-134) */
+int sv_gemm_bf16_ex(const void *A, int lda, int a_transposed, const void *B, int ldb, int b_transposed, int M, int N, int K,
+                    const float *bias, int act, const void *residual, void *out, int ldo, int out_f32, int rowmax,
+                    void *stream);
 
 /* ---- fused attention forward (tcgen05): O = softmax(Q K^T * scale + spatial gate + key mask) V, head dim 64 ---------
  * q (B,Lq,*), k/v (B,Lk,*) bf16 with batch strides *_bs and row strides *_rs (elements, % 8 == 0); head h uses columns

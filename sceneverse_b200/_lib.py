@@ -63,6 +63,8 @@ _GPS_SIGS = {
     "sv_tc05_selftest": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     "sv_gemm_bf16": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int,
                      c_int, c_int, c_void_p],
+    "sv_gemm_bf16_ex": [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p,
+                        c_void_p, c_int, c_int, c_int, c_void_p],
     "sv_attention_fwd_bf16": [c_void_p, ctypes.c_longlong, c_int, c_void_p, ctypes.c_longlong, c_int, c_void_p,
                               ctypes.c_longlong, c_int, c_void_p, ctypes.c_longlong, c_int, c_void_p, c_void_p, c_int,
                               c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p],

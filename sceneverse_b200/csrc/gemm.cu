@@ -33,6 +33,7 @@ struct GemmArgs {
   int out_f32;              // 0 bf16, 1 f32
   int rowmax;               // 0, or 16: max over groups of 16 consecutive rows (SA3 neighbourhood max)
   int ldo;                  // leading dimension of out / residual (elements)
+  int a_mn, b_mn;           // 1: the operand is stored [K][rows] (row-major, rows contiguous) = MN-major for the tensor core
 };
 
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
@@ -40,6 +41,13 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, i
       "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
       : "memory");
+}
+// MN-major SWIZZLE_128B operand staged as 64-column slabs [BK rows][128 B] (one TMA box each): 8-row groups 1024 B apart
+// (stride byte offset), consecutive 64-element MN blocks one slab (BK * 128 B) apart (leading byte offset); a K step of 16
+// rows advances the start address by 2048 B.  Same descriptor family the attention kernels use for P.V / dS.K.
+__device__ __forceinline__ uint64_t make_desc_sw128_mn(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)((BK * 128) >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         (1ull << 46) | (2ull << 61);
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -95,15 +103,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
           mbar_wait(empty + s, ph ^ 1u);  // slot free (first pass returns immediately)
           mbar_expect_tx(full + s, A_STAGE + B_STAGE);
           const int k0 = ks * BK;
-          tma_load_2d(sA + s * A_STAGE, &mapA, k0, m0, full + s);
-          tma_load_2d(sB + s * B_STAGE, &mapB, k0, n0, full + s);
+          if (g.a_mn) {  // [K][M] storage: one [BK x 64] box per 64 rows of the tile
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j) tma_load_2d(sA + s * A_STAGE + j * (BK * 128), &mapA, m0 + j * 64, k0, full + s);
+          } else {
+            tma_load_2d(sA + s * A_STAGE, &mapA, k0, m0, full + s);
+          }
+          if (g.b_mn) {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sB + s * B_STAGE + j * (BK * 128), &mapB, n0 + j * 64, k0, full + s);
+          } else {
+            tma_load_2d(sB + s * B_STAGE, &mapB, k0, n0, full + s);
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer -------------------------------
     if (lane == 0) {
-      constexpr uint32_t IDESC = make_idesc_bf16(BM, BN);
+      const uint32_t IDESC = make_idesc_bf16(BM, BN) | (g.a_mn ? 1u << 15 : 0u) | (g.b_mn ? 1u << 16 : 0u);
       uint32_t it = 0, tl = 0;
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tl) {
         const int b = tl & 1;
@@ -116,7 +134,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
           const uint32_t a0 = smem_u32(sA + s * A_STAGE), b0 = smem_u32(sB + s * B_STAGE);
 #pragma unroll
           for (int kk = 0; kk < BK / 16; ++kk)
-            mma_bf16(tmem + b * BN, make_desc_sw128(a0 + kk * 32), make_desc_sw128(b0 + kk * 32), IDESC, (ks | kk) != 0);
+            mma_bf16(tmem + b * BN, g.a_mn ? make_desc_sw128_mn(a0 + kk * 2048) : make_desc_sw128(a0 + kk * 32),
+                     g.b_mn ? make_desc_sw128_mn(b0 + kk * 2048) : make_desc_sw128(b0 + kk * 32), IDESC, (ks | kk) != 0);
           mma_commit(empty + s);  // frees the smem slot when these MMAs retire
         }
         mma_commit(acc_full + b);
@@ -292,6 +311,20 @@ int make_map(CUtensorMap *map, const void *ptr, int rows, int K, int ld, int box
   return r == CUDA_SUCCESS ? SV_OK : SV_ERR_INVALID_ARG;
 }
 
+// [K, rows] bf16 row-major with leading dimension ld (the operand's rows are the contiguous direction): box = [BK x 64]
+int make_map_mn(CUtensorMap *map, const void *ptr, int rows, int K, int ld) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return SV_ERR_CUDA;
+  cuuint64_t dims[2] = {(cuuint64_t)rows, (cuuint64_t)K};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)BK};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? SV_OK : SV_ERR_INVALID_ARG;
+}
+
 template <int BN>
 int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mb, const GemmArgs &g, cudaStream_t st) {
   constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + (2 * STAGES + 4) * 8 + 16 + 8 * STG_BYTES + 2 * BN * 4;
@@ -318,18 +351,26 @@ int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mb, const GemmArgs &g,
 
 extern "C" int sv_gemm_bf16(const void *A, int lda, const void *B, int ldb, int M, int N, int K, const float *bias,
                             int act, const void *residual, void *out, int ldo, int out_f32, int rowmax, void *stream) {
+  return sv_gemm_bf16_ex(A, lda, 0, B, ldb, 0, M, N, K, bias, act, residual, out, ldo, out_f32, rowmax, stream);
+}
+
+extern "C" int sv_gemm_bf16_ex(const void *A, int lda, int a_transposed, const void *B, int ldb, int b_transposed, int M,
+                               int N, int K, const float *bias, int act, const void *residual, void *out, int ldo,
+                               int out_f32, int rowmax, void *stream) {
   if (M < 0 || N < 0 || K < 0) return SV_ERR_INVALID_ARG;
   if (M == 0 || N == 0) return SV_OK;
-  if (!A || !B || !out || K < 8 || (K % 8) || (lda % 8) || (ldb % 8) || lda < K || ldb < K) return SV_ERR_INVALID_ARG;
+  if (!A || !B || !out || K < 8 || (lda % 8) || (ldb % 8)) return SV_ERR_INVALID_ARG;
+  if (a_transposed ? lda < M : (lda < K || (K % 8))) return SV_ERR_INVALID_ARG;
+  if (b_transposed ? ldb < N : (ldb < K || (K % 8))) return SV_ERR_INVALID_ARG;
   if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) return SV_ERR_INVALID_ARG;
   if (act < 0 || act > 2 || (rowmax != 0 && rowmax != 16) || (rowmax && residual)) return SV_ERR_INVALID_ARG;
   if (rowmax && (M % 16)) return SV_ERR_INVALID_ARG;
-  GemmArgs g{M, N, K, bias, residual, out, act, out_f32, rowmax, ldo};
+  GemmArgs g{M, N, K, bias, residual, out, act, out_f32, rowmax, ldo, a_transposed ? 1 : 0, b_transposed ? 1 : 0};
   CUtensorMap ma, mb;
   const int bn = N > 128 ? 256 : (N > 64 ? 128 : 64);
-  int rc = make_map(&ma, A, M, K, lda, BM);
+  int rc = a_transposed ? make_map_mn(&ma, A, M, K, lda) : make_map(&ma, A, M, K, lda, BM);
   if (rc) return rc;
-  rc = make_map(&mb, B, N, K, ldb, bn);
+  rc = b_transposed ? make_map_mn(&mb, B, N, K, ldb) : make_map(&mb, B, N, K, ldb, bn);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   if (bn == 256) return launch_gemm<256>(ma, mb, g, st);

@@ -99,3 +99,24 @@ def colsum(x):
                            scratch.data_ptr(), torch.cuda.current_stream(x.device).cuda_stream)
     _lib.check(lib, st, "sv_colsum")
     return out
+
+
+def gemm_ex(a, b, a_transposed=False, b_transposed=False, bias=None, act=None, out_dtype=torch.bfloat16):
+    """epilogue(A . B^T) with operands optionally given transposed in memory (no copies):
+    a: (M,K), or (K,M) when a_transposed;  b: (N,K), or (K,N) when b_transposed.  bf16 in, bf16 / f32 out (M,N)."""
+    assert a.is_cuda and a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.dim() == 2 and b.dim() == 2
+    assert a.stride(1) == 1 and b.stride(1) == 1
+    M, K = (a.shape[1], a.shape[0]) if a_transposed else a.shape
+    N, Kb = (b.shape[1], b.shape[0]) if b_transposed else b.shape
+    assert K == Kb, (a.shape, b.shape)
+    out = torch.empty((M, N), dtype=out_dtype, device=a.device)
+    if bias is not None:
+        bias = bias.float().contiguous()
+    lib = _lib.gps()
+    with torch.cuda.device(a.device):
+        st = lib.sv_gemm_bf16_ex(a.data_ptr(), a.stride(0), 1 if a_transposed else 0, b.data_ptr(), b.stride(0),
+                                 1 if b_transposed else 0, M, N, K, bias.data_ptr() if bias is not None else None, _ACT[act],
+                                 None, out.data_ptr(), N, 1 if out_dtype == torch.float32 else 0, 0,
+                                 torch.cuda.current_stream(a.device).cuda_stream)
+    _lib.check(lib, st, "sv_gemm_bf16_ex")
+    return out

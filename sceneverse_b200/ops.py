@@ -74,6 +74,13 @@ class _SpatialAttentionRecomputeFn(torch.autograd.Function):
         return gq.to(q.dtype), gk.to(k.dtype), gv.to(v.dtype), gs.to(sw.dtype), None, None, None, None
 
 
+import os as _os
+
+# opt-in: run the two backward GEMMs of every linear on the native tcgen05 GEMM with transposed (MN-major) operands
+# instead of cuBLAS.  The kernel path is parity-tested (tests/test_gemm_gpu.py::test_gemm_transposed_operands); the
+# whole-step timing with it has not been measured yet, so the default stays on the library GEMMs.
+_NATIVE_BWD_GEMM = _os.environ.get("SVB200_NATIVE_BWD_GEMM", "0") == "1"
+
 _MM_OUT_DTYPE = [None]  # does torch.mm accept out_dtype on this build? (decided at first use)
 
 
@@ -150,10 +157,15 @@ class _LinearFn(torch.autograd.Function):
             g2 = g2.to(torch.bfloat16)
         g2 = g2.contiguous()
         dx = dw = db = None
+        native_ok = _NATIVE_BWD_GEMM and x2.is_contiguous() and wb.is_contiguous()
         if ctx.needs_input_grad[0]:
-            dx = torch.mm(g2, wb).view(ctx.in_shape).to(ctx.in_dtype)
+            # dgrad: (M,N) . (N,Kin) — the weight is the transposed (MN-major) B operand
+            dx = native.gemm_ex(g2, wb, b_transposed=True) if native_ok else torch.mm(g2, wb)
+            dx = dx.view(ctx.in_shape).to(ctx.in_dtype)
         if ctx.needs_input_grad[1]:
-            dw = _mm_f32(g2.t(), x2)
+            # wgrad: g^T (N,M) . x (M,Kin) — both operands transposed in memory, fp32 result
+            dw = native.gemm_ex(g2, x2, a_transposed=True, b_transposed=True, out_dtype=torch.float32) if native_ok \
+                else _mm_f32(g2.t(), x2)
         if ctx.needs_input_grad[2]:
             db = native.colsum(g2)
         return dx, dw, db

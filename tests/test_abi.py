@@ -68,3 +68,20 @@ def test_dropin_import_name(built):
         assert callable(getattr(_ext, fn))
     sys.modules.pop("pointnet2", None)
     sys.modules.pop("pointnet2._ext", None)
+
+
+def test_gps_argument_validation_without_gpu(built):
+    """libsvgps rejects malformed calls before touching the device (status 1 = SV_ERR_INVALID_ARG, 0 for empty work)."""
+    from sceneverse_b200 import _lib
+    lib = _lib.gps()
+    fake = 0x1000  # 16-byte aligned, never dereferenced: validation fails first
+    # transposed A needs lda >= M and lda % 8 == 0; K-major operands need K % 8 == 0
+    assert lib.sv_gemm_bf16_ex(fake, 777, 1, fake, 320, 1, 777, 320, 1000, None, 0, None, fake, 320, 1, 0, None) == 1
+    assert lib.sv_gemm_bf16_ex(fake, 130, 0, fake, 2048, 1, 64, 2048, 130, None, 0, None, fake, 2048, 1, 0, None) == 1
+    assert lib.sv_gemm_bf16_ex(fake, 64, 0, fake, 64, 0, 0, 64, 64, None, 0, None, fake, 64, 0, 0, None) == 0
+    assert lib.sv_layer_norm_fwd(fake, None, 1, 4, 770, fake, fake, 1e-5, 0.0, 0, fake, None, fake, fake, None) == 1   # D % 8
+    assert lib.sv_layer_norm_fwd(fake, fake, 1, 4, 768, fake, fake, 1e-5, 0.0, 0, fake, None, fake, fake, None) == 1  # residual needs s
+    assert lib.sv_colsum(fake, 100, 1, 4, 100, fake, fake, None) == 1                                                # N % 8
+    assert lib.sv_attention_fwd_dropout_bf16(fake, 8, 8, fake, 8, 8, fake, 8, 8, fake, 8, 8, None, None, 0, None, 1, 12, 4,
+                                             400, 0.125, None, 0.0, 0, None) == 1                                      # Lk > 384
+    assert lib.sv_layer_norm_scratch_floats(768) > 0 and lib.sv_colsum_scratch_floats(768) > 0

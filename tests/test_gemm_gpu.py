@@ -60,3 +60,20 @@ def test_gemm_strided_rows_and_rowmax():
     want = torch.relu(a.float() @ w.float().t() + bias).view(32, 16, 256).max(dim=1).values
     assert got.shape == (32, 256)
     assert (got - want).abs().max().item() / want.abs().max().item() < 2e-3
+
+
+@pytest.mark.parametrize("M,N,K,at,bt", [(128, 64, 64, 0, 1), (128, 64, 64, 1, 1), (128, 64, 64, 1, 0),
+                                         (200, 136, 72, 0, 1), (200, 136, 72, 1, 1), (200, 136, 72, 1, 0),
+                                         (384, 768, 3072, 0, 1), (384, 768, 3072, 1, 1), (384, 768, 3072, 1, 0),
+                                         (777, 320, 1000, 0, 1), (64, 2048, 130, 1, 1)])
+def test_gemm_transposed_operands(M, N, K, at, bt):
+    """sv_gemm_bf16_ex: operands given transposed in memory are staged as 64-column slabs and read MN-major by the tensor
+    core (the dgrad / wgrad forms of a linear layer) — against an fp32 torch matmul of the same bf16 values."""
+    from sceneverse_b200 import native
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    def rnd(*s): return (torch.randn(*s, device="cuda", generator=g) * 0.5).bfloat16()
+    A = rnd(K, M) if at else rnd(M, K)
+    B = rnd(K, N) if bt else rnd(N, K)
+    want = (A.float().t() if at else A.float()) @ (B.float() if bt else B.float().t())
+    got = native.gemm_ex(A, B, a_transposed=bool(at), b_transposed=bool(bt), out_dtype=torch.float32)
+    assert (got - want).abs().max().item() <= 2e-3 * want.abs().max().item()
