@@ -109,6 +109,21 @@ class PretrainStep:
     def parameters(self):
         return [p for p in self.module.parameters() if p.requires_grad]
 
+    def close(self):
+        """Unregister the process-wide hooks of graph mode (the dropout seed counter lives in this object's memory, the
+        bf16 weight shadows reference its parameters)."""
+        if getattr(self, "_step_counter", None) is not None:
+            try:
+                from . import _lib
+                _lib.gps().sv_dropout_seed_offset(None)
+            except Exception:
+                pass
+            self._step_counter = None
+            ops.clear_shadows()
+
+    def __del__(self):
+        self.close()
+
     # ---- CUDA-graph path ---------------------------------------------------------------------------------------------
     def _raw_fwd_bwd(self):
         self._step_counter.add_(1)
