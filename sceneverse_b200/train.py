@@ -113,16 +113,19 @@ class PretrainStep:
         """Unregister the process-wide hooks of graph mode (the dropout seed counter lives in this object's memory, the
         bf16 weight shadows reference its parameters)."""
         if getattr(self, "_step_counter", None) is not None:
+            self._step_counter = None
             try:
                 from . import _lib
                 _lib.gps().sv_dropout_seed_offset(None)
-            except Exception:
+                ops.clear_shadows()
+            except Exception:      # interpreter shutdown: modules may already be gone
                 pass
-            self._step_counter = None
-            ops.clear_shadows()
 
     def __del__(self):
-        self.close()
+        try:
+            self.close()
+        except Exception:
+            pass
 
     # ---- CUDA-graph path ---------------------------------------------------------------------------------------------
     def _raw_fwd_bwd(self):
