@@ -97,10 +97,67 @@ def golden_gps_stack():
     print({k: (v.shape if hasattr(v, "shape") else v) for k, v in out.items()})
 
 
+def golden_gps_backward():
+    """Backward parity fixture: the UNMODIFIED reference vision encoder (frozen PointNet++, trainable spatial layers) ->
+    UnifiedSpatialCrossEncoderV2 -> GroundHeadV1 + OVPretrainHead -> lm + within + obj-between + scene-between + og3d
+    losses, eval mode (no dropout), fp32 CPU; stores the loss, the gradient norm of EVERY trainable parameter and a few
+    gradient slices.  tests/test_gps_modules.py replays it with the B200 classes."""
+    import importlib
+    import types
+    from modules.build import GROUNDING_REGISTRY, HEADS_REGISTRY, VISION_REGISTRY
+    CL = importlib.import_module("optim.loss.contra_loss")
+    LL = importlib.import_module("optim.loss.loss")
+    d = synthetic.scene_batch(33, B=2, O=16, P=1024, L=50, Ls=300, min_obj=6)
+    t = {k: torch.from_numpy(v) for k, v in d.items()}
+    g = torch.Generator().manual_seed(7)
+    txt = torch.randn(2, 50, 768, generator=g) * 0.5
+    scene_txt = torch.randn(2, 768, generator=g) * 0.5
+    cfg = types.SimpleNamespace(num_gpu=1, task="Pretrain")
+    with tempfile.TemporaryDirectory() as tmp, ref_shims.cpu_cuda_identity():
+        ref_shims.write_text_features(tmp, weights.synthetic_tensor("text_features", (607, 768)))
+        mods = {
+            "enc": _load(VISION_REGISTRY.get("PointOpenVocabEncoder")(None, lang_path=tmp, freeze=True)),
+            "v2": _load(GROUNDING_REGISTRY.get("UnifiedSpatialCrossEncoderV2")(None), 1),
+            "gh": _load(HEADS_REGISTRY.get("GroundHeadV1")(None, input_size=768, hidden_size=384, sem_cls_size=607), 4),
+            "ph": _load(HEADS_REGISTRY.get("OVPretrainHead")(None), 5),
+            "l_within": CL.TextObjWithinBatch(cfg), "l_obj": CL.TextObjBetweenBatch(cfg), "l_scene": CL.TextSceneBetweenBatch(cfg),
+        }
+        pn = {}
+        hk = mods["enc"].point_feature_extractor.register_forward_hook(lambda m, a, o: pn.__setitem__("out", o.detach()))
+        obj, obj_pre, sem = mods["enc"](t["obj_fts"], t["obj_locs"], t["obj_masks"], t["obj_sem_masks"], t["obj_labels"], 1, 1)
+        hk.remove()
+        t2, o2 = mods["v2"](txt, t["txt_masks"], obj, t["obj_locs"], t["obj_masks"])
+        _, _, _, og = mods["gh"](t2, o2, obj_pre, t["obj_masks"])
+        lm, _ = mods["ph"](t2, o2)
+        dd = dict(t)
+        dd.update(intra_obj_embeds=o2, intra_text_embed=t2[:, 0], inter_obj_embeds=obj, inter_text_embed=txt[:, 0],
+                  scene_embed=obj.mean(dim=1), scene_text_embed=scene_txt, og3d_logits=og, txt_lm_cls_logits=lm)
+        parts = {"lm": LL.lm_cls_loss(dd), "within": mods["l_within"](dd), "obj_between": mods["l_obj"](dd),
+                 "scene_between": mods["l_scene"](dd), "og3d": LL.og3d_loss(dd)}
+        total = sum(parts.values())
+        total.backward()
+    norms, slices = {}, {}
+    for mname, m in mods.items():
+        for n, p in m.named_parameters():
+            if p.grad is not None:
+                norms[f"{mname}.{n}"] = float(p.grad.double().norm())
+    for key in ["v2.unified_encoder.0.self_attn.in_proj_weight", "enc.spatial_encoder.0.self_attn.lang_cond_fc.weight",
+                "ph.lm_pred_head.transform.dense.weight", "gh.og3d_head.0.weight", "enc.spatial_encoder.3.norm2.bias"]:
+        mname, n = key.split(".", 1)
+        slices[key] = dict(mods[mname].named_parameters())[n].grad.reshape(-1)[:96].numpy()
+    np.savez_compressed(os.path.join(OUT, "model_gps_grads.npz"), data_seed=33, txt_seed=7, total=total.detach().numpy(),
+                        pn_out=pn["out"].numpy(),   # frozen PointNet++ features: lets a CPU test skip the CUDA-only backbone
+                        **{"loss_" + k: v.detach().numpy() for k, v in parts.items()},
+                        **{"slice:" + k: v for k, v in slices.items()})
+    json.dump(norms, open(os.path.join(OUT, "model_gps_grad_norms.json"), "w"), indent=0, sort_keys=True)
+    print("backward golden:", float(total), len(norms), "parameter gradients")
+
+
 def main():
     ref_shims.install()
     torch.manual_seed(0)
     golden_gps_stack()
+    golden_gps_backward()
     shapes = {"PointNetPP": golden_pointnetpp()}
     # state_dict contracts of the registry classes (SURVEY.md §8b): key -> shape
     from modules.build import GROUNDING_REGISTRY, HEADS_REGISTRY, VISION_REGISTRY
