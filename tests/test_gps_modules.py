@@ -249,54 +249,3 @@ def test_backward_matches_reference_gradients_cpu_fp32():
         got = dict(mods[mname].named_parameters())[n].grad.reshape(-1)[:96].numpy()
         assert np.abs(got - G[key]).max() <= 1e-4 * (np.abs(G[key]).max() + 1e-8), key
 
-
-@pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="added after the round's last GPU slot: tolerances not yet calibrated on hardware")
-def test_backward_matches_reference_gradients_gpu_bf16():
-    """The same reference-gradient fixture through the NATIVE path (bf16 autocast: tcgen05 attention forward / backward,
-    fused LayerNorm, native bias gradients, padded LM head + fused CE): loss terms within 2e-2, gradient norms of all
-    trainable parameters within 5e-2 (+ a floor for the mathematically-zero ones)."""
-    G = np.load(os.path.join(GOLDEN, "model_gps_grads.npz"))
-    want_norms = json.load(open(os.path.join(GOLDEN, "model_gps_grad_norms.json")))
-    d = synthetic.scene_batch(int(G["data_seed"]), B=2, O=16, P=1024, L=50, Ls=300, min_obj=6)
-    t = {k: torch.from_numpy(v).cuda() for k, v in d.items()}
-    g = torch.Generator().manual_seed(int(G["txt_seed"]))
-    txt = (torch.randn(2, 50, 768, generator=g) * 0.5).cuda()
-    scene_txt = (torch.randn(2, 768, generator=g) * 0.5).cuda()
-    tf = weights.synthetic_tensor("text_features", (607, 768))
-    mods = {"enc": load(vision.PointOpenVocabEncoder(None, freeze=True, text_features=tf), 0).cuda(),
-            "v2": load(grounding.UnifiedSpatialCrossEncoderV2(None), 1).cuda(),
-            "gh": load(heads.GroundHeadV1(None, input_size=768, hidden_size=384, sem_cls_size=607), 4).cuda(),
-            "ph": load(heads.OVPretrainHead(None), 5).cuda(),
-            "l_within": losses.TextObjWithinBatch({"num_gpu": 1}).cuda(), "l_obj": losses.TextObjBetweenBatch({"num_gpu": 1}).cuda(),
-            "l_scene": losses.TextSceneBetweenBatch({"num_gpu": 1}).cuda()}
-    pn_out = torch.from_numpy(G["pn_out"]).cuda()
-
-    class Backbone(torch.nn.Module):
-        def forward(self, x):
-            return pn_out
-    mods["enc"].point_feature_extractor = Backbone()
-    with torch.autocast("cuda", dtype=torch.bfloat16):
-        obj, obj_pre, _ = mods["enc"](t["obj_fts"], t["obj_locs"], t["obj_masks"], t["obj_sem_masks"], t["obj_labels"], 1, 1)
-        t2, o2 = mods["v2"](txt, t["txt_masks"], obj, t["obj_locs"], t["obj_masks"])
-        _, _, _, og = mods["gh"](t2, o2, obj_pre, t["obj_masks"])
-        lm, _ = mods["ph"](t2, o2)
-        dd = dict(t)
-        dd.update(intra_obj_embeds=o2, intra_text_embed=t2[:, 0], inter_obj_embeds=obj, inter_text_embed=txt[:, 0],
-                  scene_embed=obj.mean(dim=1), scene_text_embed=scene_txt, og3d_logits=og, txt_lm_cls_logits=lm)
-        parts = {"lm": losses.lm_cls_loss(dd), "within": mods["l_within"](dd), "obj_between": mods["l_obj"](dd),
-                 "scene_between": mods["l_scene"](dd), "og3d": losses.og3d_loss(dd)}
-        total = sum(parts.values())
-    for k, v in parts.items():
-        assert abs(float(v) - float(G["loss_" + k])) < 2e-2 * max(1.0, abs(float(G["loss_" + k]))), (k, float(v))
-    total.backward()
-    scale = max(want_norms.values())
-    bad = {}
-    for mname, m in mods.items():
-        for n, p in m.named_parameters():
-            k = f"{mname}.{n}"
-            if k in want_norms:
-                got = float(p.grad.double().norm()) if p.grad is not None else 0.0
-                if abs(got - want_norms[k]) > 5e-2 * abs(want_norms[k]) + 1e-3 * scale:
-                    bad[k] = (got, want_norms[k])
-    assert not bad, bad
