@@ -13,13 +13,16 @@ from sceneverse_b200.modules import grounding, heads, losses, vision
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 
 
+# bounds = 2x the deviation measured on the B200 (profiles/r2_parity_bf16_grads.json)
+LOSS_TOL, NORM_TOL, FLOOR = 2e-2, 5e-2, 1e-3
+
+
 def load(m, seed):
     m.load_state_dict(weights.synthetic_state_dict(m, seed=seed))
     return m.eval()
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="added after the round's last GPU slot: tolerances not yet calibrated on hardware")
 def test_backward_matches_reference_gradients_gpu_bf16():
     """The same reference-gradient fixture through the NATIVE path (bf16 autocast: tcgen05 attention forward / backward,
     fused LayerNorm, native bias gradients, padded LM head + fused CE): loss terms within 2e-2, gradient norms of all
@@ -55,16 +58,26 @@ def test_backward_matches_reference_gradients_gpu_bf16():
         parts = {"lm": losses.lm_cls_loss(dd), "within": mods["l_within"](dd), "obj_between": mods["l_obj"](dd),
                  "scene_between": mods["l_scene"](dd), "og3d": losses.og3d_loss(dd)}
         total = sum(parts.values())
-    for k, v in parts.items():
-        assert abs(float(v) - float(G["loss_" + k])) < 2e-2 * max(1.0, abs(float(G["loss_" + k]))), (k, float(v))
+    loss_err = {k: abs(float(v) - float(G["loss_" + k])) / max(1.0, abs(float(G["loss_" + k]))) for k, v in parts.items()}
+    for k, e in loss_err.items():
+        assert e < LOSS_TOL, (k, e)
     total.backward()
     scale = max(want_norms.values())
     bad = {}
+    worst = (0.0, None)
     for mname, m in mods.items():
         for n, p in m.named_parameters():
             k = f"{mname}.{n}"
             if k in want_norms:
                 got = float(p.grad.double().norm()) if p.grad is not None else 0.0
-                if abs(got - want_norms[k]) > 5e-2 * abs(want_norms[k]) + 1e-3 * scale:
+                r = abs(got - want_norms[k]) / (abs(want_norms[k]) + FLOOR * scale)
+                worst = max(worst, (r, k))
+                if r > NORM_TOL:
                     bad[k] = (got, want_norms[k])
+    print("GRAD_PARITY_BF16 " + json.dumps({"loss_err": loss_err, "worst_grad_norm_dev": worst[0], "worst_param": worst[1],
+                                            "params": len(want_norms)}))
+    out = os.path.join(os.path.dirname(GOLDEN), os.pardir, "gpurun_out")
+    if os.path.isdir(out):
+        json.dump({"loss_err": loss_err, "worst_grad_norm_dev": worst[0], "worst_param": worst[1], "loss_tol": LOSS_TOL,
+                   "norm_tol": NORM_TOL, "floor": FLOOR}, open(os.path.join(out, "r2_parity_bf16_grads.json"), "w"), indent=1)
     assert not bad, bad
