@@ -69,6 +69,11 @@ def install():
 
         om.OmegaConf = OmegaConf
         sys.modules["omegaconf"] = om
+    if "clip" not in sys.modules:   # model/objcls.py:6 imports it at module level (tokeniser only; never called here)
+        try:
+            import clip  # noqa: F401
+        except ImportError:
+            sys.modules["clip"] = types.ModuleType("clip")
     builtins.__POINTNET2_SETUP__ = True
     if REF_ROOT not in sys.path:
         sys.path.insert(0, REF_ROOT)

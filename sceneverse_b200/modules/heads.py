@@ -87,3 +87,51 @@ class OVPretrainHead(nn.Module):
 
     def forward(self, txt_embeds, obj_embeds, **kwargs):
         return self.lm_pred_head(txt_embeds), self.obj_pred_head(obj_embeds)
+
+
+class _AttentionPool(nn.Module):
+    """Masked soft-attention pooling over a token axis followed by a merge projection (reference: qa_head.py:42-70;
+    parameter names `mlp.fc.linear.*`, `mlp.linear.*`, `linear_merge.*` kept for checkpoint compatibility).  One score
+    MLP (hidden -> mid -> glimpses, GELU + dropout), scores of masked tokens set to -1e9 before the softmax over tokens;
+    the glimpse-weighted sums are one batched contraction instead of the reference's per-glimpse loop + cat."""
+
+    def __init__(self, hidden_size, mid_size=512, glimpses=1, out_size=1024, pdrop=0.1):
+        super().__init__()
+        self.mlp = nn.Module()
+        self.mlp.fc = nn.Module()
+        self.mlp.fc.linear = nn.Linear(hidden_size, mid_size)
+        self.mlp.linear = nn.Linear(mid_size, glimpses)
+        self.linear_merge = nn.Linear(hidden_size * glimpses, out_size)
+        self.pdrop = pdrop
+
+    def forward(self, x, pad_mask):
+        h = ops.linear(x, self.mlp.fc.linear.weight, self.mlp.fc.linear.bias, activation="gelu")
+        if self.pdrop > 0:
+            h = nn.functional.dropout(h, self.pdrop, self.training)
+        att = ops.linear(h, self.mlp.linear.weight, self.mlp.linear.bias)            # (B, L, G)
+        if pad_mask is not None:
+            att = att.masked_fill(pad_mask.unsqueeze(2), -1e9)
+        att = torch.softmax(att.float(), dim=1).to(x.dtype)
+        pooled = torch.einsum("blg,bld->bgd", att, x).flatten(1)                      # glimpse-major, like the cat
+        return ops.linear(pooled, self.linear_merge.weight, self.linear_merge.bias)
+
+
+@HEADS_REGISTRY.register()
+class QAHeadV1(nn.Module):
+    """ScanQA / SQA3D answer head (reference: modules/heads/qa_head.py:72-90): attention-pool the object and the text
+    tokens, LayerNorm(sum), 2-layer GELU classifier over the answer vocabulary.  Same constructor, forward contract
+    (obj_embeds, obj_masks, txt_embeds, txt_masks; masks True = valid) and state_dict keys."""
+
+    def __init__(self, cfg, hidden_size=768, mlp_size=256, glimpse=1, flat_out_size=512, num_answers=8864):
+        super().__init__()
+        self.attflat_visual = _AttentionPool(hidden_size, mlp_size, glimpse, flat_out_size, 0.1)
+        self.attflat_lang = _AttentionPool(hidden_size, mlp_size, glimpse, flat_out_size, 0.1)
+        self.answer_cls = nn.Sequential(nn.Linear(flat_out_size, hidden_size), nn.GELU(), nn.Dropout(0.3),
+                                        nn.Linear(hidden_size, num_answers))
+        self.fusion_norm = LayerNorm(flat_out_size)
+
+    def forward(self, obj_embeds, obj_masks, txt_embeds, txt_masks, **kwargs):
+        object_feat = self.attflat_visual(obj_embeds, obj_masks.logical_not())
+        lang_feat = self.attflat_lang(txt_embeds, txt_masks.logical_not())
+        fuse = self.fusion_norm(lang_feat, residual=object_feat)
+        return self.answer_cls(fuse)
