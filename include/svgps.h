@@ -53,6 +53,29 @@ int sv_gemm_bf16_ex(const void *A, int lda, int a_transposed, const void *B, int
                     const float *bias, int act, const void *residual, void *out, int ldo, int out_f32, int rowmax,
                     void *stream);
 
+/* ---- the three GEMMs of a linear layer y = x W^T + b with their fused epilogues (same tcgen05 kernel family) ------
+ * Replace F.linear and its autograd (AddmmBackward: mm, mm, sum) for every nn.Linear of the attention stack, BERT and the
+ * heads (reference: modules/layers/transformers.py:115-154,188-192,285-316; modules/language/bert.py:21-26).
+ * x (M,K) bf16 ld ldx; w (N,K) bf16 ld ldw (nn.Linear layout); all leading dimensions % 8 == 0, 16-byte aligned bases.
+ * forward:  out = dropout_p(act(x w^T + bias)) -> (M,N) bf16 | f32, ld ldo; act 0 none / 1 relu / 2 gelu(erf);
+ *           pre_out (bf16, ld ldo, may be NULL) receives x w^T + bias before the activation (saved for the gelu backward);
+ *           the dropout mask is the counter hash of csrc/attn_common.cuh keyed by (seed, row, column): nothing is stored. */
+int sv_linear_fwd_bf16(const void *x, int ldx, const void *w, int ldw, int M, int N, int K, const float *bias, int act,
+                       float dropout_p, unsigned long long seed, void *out, int ldo, int out_f32, void *pre_out,
+                       void *stream);
+/* dgrad:    dx (M,Kin) = (gy (M,N) . w (N,Kin)) x f, the weight read as a transposed (MN-major) operand, no copy.
+ *           dact 0: f = 1.  dact 1: aux = the forward OUTPUT of a relu(+dropout) layer of shape (M,Kin): f = aux > 0 ? 1/(1-p) : 0.
+ *           dact 2: aux = the saved PRE-activation of a gelu(+dropout) layer: f = gelu'(aux) x mask(seed,row,col)/(1-p).
+ *           (the activation sits on the INPUT side of this linear: h = dropout(act(pre)), y = h w^T) */
+int sv_linear_dgrad_bf16(const void *gy, int ldg, const void *w, int ldw, int M, int N, int Kin, int dact, const void *aux,
+                         int ld_aux, float dropout_p, unsigned long long seed, void *dx, int ldx, int out_f32, void *stream);
+/* wgrad:    dw (N,Kin) f32 (ld ld_dw) (+)= gy^T . x and db (N) f32 (+)= column sums of gy (db may be NULL), contraction over
+ *           the M tokens split across the grid, results reduced with red.global.add — accumulate = 1 adds straight into an
+ *           existing gradient buffer (the flat fp32 buffer the data-parallel all-reduce runs on), 0 overwrites.  The bias
+ *           gradient costs one extra N = 16 MMA per K step against a tile of ones in the same main loop. */
+int sv_linear_wgrad_bf16(const void *gy, int ldg, const void *x, int ldx, int M, int N, int Kin, float *dw, int ld_dw,
+                         float *db, int accumulate, void *stream);
+
 /* ---- fused attention forward (tcgen05): O = softmax(Q K^T * scale + spatial gate + key mask) V, head dim 64 ---------
  * q (B,Lq,*), k/v (B,Lk,*) bf16 with batch strides *_bs and row strides *_rs (elements, % 8 == 0); head h uses columns
  * [64h, 64h+64).  key_padding_mask (B,Lk) bytes, 1 = ignore (may be NULL).  spatial_w (B,Lq,spatial_heads*6) f32 =
@@ -144,6 +167,28 @@ int sv_cross_entropy_fwd_bwd(const void *logits, long long row_stride, int is_bf
 int sv_cross_entropy_fwd_bwd_strided(const void *logits, long long row_stride, int is_bf16, const long long *labels, int R,
                                      int V, long long ignore_index, float *loss_rows, void *grad_logits,
                                      long long grad_row_stride, void *stream);
+
+/* Backward of a stand-alone activation behind a linear layer (the FFN form fuses this into sv_linear_dgrad_bf16):
+ * out = g x act'(.), (M,N) bf16, N % 8 == 0.  mode 1: relu, aux = forward output; mode 2: gelu(erf), aux = pre-activation. */
+int sv_act_bwd_bf16(const void *g, int ldg, const void *aux, int ld_aux, int mode, int M, int N, void *out, int ldo,
+                    void *stream);
+
+/* Gradient of an embedding lookup: dw[ids[t]][:] += grad_out[t][:] (fp32 red.add; rows with ids == padding_idx skipped).
+ * grad_out (ntok, D) bf16 | f32 with row stride ldg; dw (vocab, D) f32 contiguous, NOT zeroed here (accumulates).
+ * (reference: autograd of the three nn.Embedding tables of HF BertEmbeddings, modules/language/bert.py:21-26) */
+int sv_embedding_bwd(const void *grad_out, long long ldg, int is_bf16, const long long *ids, int ntok, int D, long long vocab,
+                     long long padding_idx, float *dw, void *stream);
+
+/* clip_grad_norm_ + AdamW + bf16 shadow refresh over FLAT buffers in two launches (squared-norm partials, then the update;
+ * reference: trainer/build.py:135-145, optim/utils.py:1-18).  params / exp_avg / exp_avg_sq / grads: n f32, 16-byte aligned;
+ * shadow_bf16: n bf16 (may be NULL).  segments: DEVICE array of nseg records {long long begin, end; float lr_scale,
+ * weight_decay} (element ranges, multiples of 4) — lr of a segment = base_lr * lr_scale * *lr_factor.  step: device 1-based
+ * step counter (bias correction).  scratch: sv_adamw_scratch_floats() floats.  norm_out (may be NULL) receives ||g||.
+ * max_norm <= 0 disables clipping. */
+int sv_adamw_scratch_floats(void);
+int sv_adamw_flat(float *params, float *exp_avg, float *exp_avg_sq, const float *grads, void *shadow_bf16, long long n,
+                  const void *segments, int nseg, float max_norm, const float *lr_factor, const long long *step, float base_lr,
+                  float beta1, float beta2, float eps, float *scratch, float *norm_out, void *stream);
 
 /* L2-normalise + all-gather fused over NVLink peer memory (reference: contra_loss.py:58-64,86-91 + dist_utils.py:131-149).
  * a, b: local (n,D) f32.  peer_bufs[world] / peer_signals[world]: DEVICE arrays of device pointers into a symmetric

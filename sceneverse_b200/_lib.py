@@ -99,6 +99,17 @@ _GPS_SIGS = {
     "sv_dropout_seed_offset": [c_void_p],
     "sv_colsum": [c_void_p, ctypes.c_longlong, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
     "sv_colsum_scratch_floats": [c_int],
+    "sv_linear_fwd_bf16": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_float, ctypes.c_ulonglong,
+                           c_void_p, c_int, c_int, c_void_p, c_void_p],
+    "sv_linear_dgrad_bf16": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_float,
+                             ctypes.c_ulonglong, c_void_p, c_int, c_int, c_void_p],
+    "sv_linear_wgrad_bf16": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p],
+    "sv_act_bwd_bf16": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p],
+    "sv_embedding_bwd": [c_void_p, ctypes.c_longlong, c_int, c_void_p, c_int, c_int, ctypes.c_longlong, ctypes.c_longlong,
+                         c_void_p, c_void_p],
+    "sv_adamw_scratch_floats": [],
+    "sv_adamw_flat": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_void_p, c_int, c_float, c_void_p,
+                      c_void_p, c_float, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p],
     "sv_sa_mlp_param_bytes": [c_int],
     "sv_sa1_mlp_bf16": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
     "sv_sa2_mlp_bf16": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],

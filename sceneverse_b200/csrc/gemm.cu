@@ -1,18 +1,30 @@
-// Persistent, warp-specialised tcgen05 GEMM with fused epilogues — the dense-contraction workhorse of the GPS path
-// (every nn.Linear of the attention stack / heads and the SA3 + fc stage of PointNet++; reference: F.linear /
-// 1x1 Conv2d call sites listed in SURVEY.md §2.3).
+// Persistent, warp-specialised tcgen05 GEMM with fused epilogues — the dense-contraction workhorse of the GPS path:
+// every nn.Linear of the attention stack / BERT / heads in all three directions (forward, dgrad, wgrad) and the
+// SA3 + fc stage of PointNet++ (reference: F.linear / 1x1 Conv2d call sites and their autograd, SURVEY.md §2.3,
+// e.g. modules/layers/transformers.py:115-154,188-192,285-316).
 //
-//   C[M,N] = epilogue( A[M,K] (bf16, row-major)  x  B[N,K]^T (bf16, row-major = nn.Linear weight layout) )
+//   C[M,N] = epilogue( A[M,K] x B[N,K]^T ),  bf16 operands, fp32 accumulation in TMEM
 //
 // Roles (320 threads): warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator + MMA issuer (one lane),
-// warps 2..9 = epilogue (two warps per TMEM lane quadrant, each thread one accumulator row x half of the columns).  Operand tiles travel global -> shared by TMA
-// (cp.async.bulk.tensor.2d, one box of [rows x 64 elements] = 128-byte rows, SWIZZLE_128B, read back by the tensor core
-// through a SWIZZLE_128B K-major UMMA descriptor) through a 4-stage mbarrier ring; accumulators are double-buffered
-// in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.  Out-of-bounds rows / columns / K are zero-filled by
-// TMA, the epilogue masks its stores.
+// warps 2..9 = epilogue (two warps per TMEM lane quadrant, each thread one accumulator row x half of the columns).
+// Operand tiles travel global -> shared by TMA (cp.async.bulk.tensor.2d, 128-byte rows, SWIZZLE_128B) through a 4-stage
+// mbarrier ring; either operand may be stored transposed in memory ([K][rows]) and is then staged as 64-column slabs and
+// read MN-major by the tensor core — the dgrad / wgrad forms of a linear layer need no transposed copy.  Accumulators
+// are double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.  Out-of-bounds rows / columns /
+// K are zero-filled by TMA, the epilogue masks its stores.
+//
+// Epilogue families (template parameter EPI):
+//   EPI_FWD   + bias -> (store pre-activation copy) -> relu | gelu(erf) -> dropout (counter hash, nothing stored)
+//             -> + residual -> bf16 | f32 store, or max over 16-row groups (PointNet++ SA3 neighbourhood max)
+//   EPI_DGRAD x activation derivative: relu+dropout from the saved forward OUTPUT (h > 0 ? 1/keep : 0), or gelu' from the
+//             saved pre-activation with the dropout mask regenerated from (seed, row, column)
+//   EPI_WGRAD fp32 result, split-K over the work list, `red.global.add.v4.f32` straight into the (flat) gradient buffer;
+//             the bias gradient (column sums of dL/dy) comes out of the SAME main loop: one extra N = 16 MMA per K step
+//             against a constant tile of ones, accumulated in 32 spare TMEM columns (first column-tile only)
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include "attn_common.cuh"
 #include "svcommon.h"
 #include "svgps.h"
 #include "tc05.cuh"
@@ -23,17 +35,28 @@ using namespace tc05;
 
 constexpr int BM = 128, BK = 64, STAGES = 4;
 constexpr int STG_BYTES = 32 * 80;  // per epilogue warp: 32 rows x (64 B + 16 B pad); also holds the [32][17] f32 row-max scratch
+constexpr int EPI_FWD = 0, EPI_DGRAD = 1, EPI_WGRAD = 2;
 
 struct GemmArgs {
   int M, N, K;
-  const float *bias;        // [N] or null
-  const void *residual;     // [M,N] same dtype as out, or null (added after the activation)
+  const float *bias;        // [N] or null (FWD)
+  const void *residual;     // [M,N] same dtype as out, or null (FWD; added after activation / dropout)
   void *out;                // [M,N] (or [M/rowmax,N] when rowmax > 0)
-  int act;                  // 0 none, 1 relu, 2 gelu(erf)
+  int act;                  // FWD: 0 none, 1 relu, 2 gelu(erf);  DGRAD: 0 none, 1 relu(+dropout) from output, 2 gelu(+dropout) from pre-activation
   int out_f32;              // 0 bf16, 1 f32
   int rowmax;               // 0, or 16: max over groups of 16 consecutive rows (SA3 neighbourhood max)
-  int ldo;                  // leading dimension of out / residual (elements)
+  int ldo;                  // leading dimension of out / residual / out2 (elements)
   int a_mn, b_mn;           // 1: the operand is stored [K][rows] (row-major, rows contiguous) = MN-major for the tensor core
+  void *out2;               // FWD: bf16 [M,N] (ld = ldo) copy of the pre-activation (acc + bias), or null
+  const void *aux;          // DGRAD: bf16 [M,N] saved forward tensor (act 1: output, act 2: pre-activation)
+  int ld_aux;
+  uint32_t t16;             // dropout threshold (0 = no dropout): keep iff 16-bit uniform >= t16
+  float inv_keep;
+  unsigned long long seed;
+  const unsigned long long *seed_offset;
+  int splits;               // split-K factor (>= 1); > 1 only with red_out
+  int red_out;              // WGRAD: accumulate into out with red.global.add instead of storing
+  float *bias_grad;         // WGRAD: [M] += row sums of A (the bias gradient), or null
 };
 
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
@@ -52,16 +75,112 @@ __device__ __forceinline__ uint64_t make_desc_sw128_mn(uint32_t smem_addr) {
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ void red_add_v4(float *p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+// Phi(x) = 0.5 (1 + erf(x / sqrt 2)) and e = exp(-x^2 / 2) with two MUFU ops: erf by Abramowitz-Stegun 7.1.26
+// (|error| < 1.5e-7, far below the bf16 / fp32-accumulation noise of the GEMM it follows); gelu = x Phi,
+// gelu' = Phi + x e / sqrt(2 pi) — the exact (erf) GELU the reference uses (F.gelu default, HF "gelu").
+__device__ __forceinline__ void gelu_parts(float x, float &cdf, float &e) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  const float p = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
+  e = attn::ex2f(-z * z * 1.4426950408889634f);
+  const float h = 0.5f * p * e;          // = 0.5 (1 - erf|z|)
+  cdf = x >= 0.f ? 1.0f - h : h;
+}
+__device__ __forceinline__ float gelu_erf(float x) {
+  float c, e;
+  gelu_parts(x, c, e);
+  return x * c;
+}
+__device__ __forceinline__ float gelu_grad(float x) {
+  float c, e;
+  gelu_parts(x, c, e);
+  return fmaf(x * e, 0.3989422804014327f, c);
+}
 
-template <int BN>
+// ---- chunk stores: a warp's 32 rows x 32 columns leave through a per-warp [32][80 B] staging buffer so that one store
+// instruction writes 8 rows x 64 B instead of 32 scattered 16-byte pieces ---------------------------------------------------
+template <bool RED>
+__device__ __forceinline__ void store_chunk_f32(const float (&v)[32], float *ob, int ldo, const float *res, int M, int N,
+                                                int row, int wrow0, int col0, uint8_t *stg, int lane) {
+  const bool vec_ok = col0 + 32 <= N && res == nullptr && (reinterpret_cast<uintptr_t>(ob) & 15) == 0 && (ldo & 3) == 0 &&
+                      (col0 & 3) == 0;
+  if (vec_ok) {
+    const int sr = lane >> 2, seg = lane & 3;
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        *reinterpret_cast<float4 *>(stg + lane * 80 + k * 16) =
+            make_float4(v[hh * 16 + 4 * k], v[hh * 16 + 4 * k + 1], v[hh * 16 + 4 * k + 2], v[hh * 16 + 4 * k + 3]);
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int r = it * 8 + sr;
+        const float4 w = *reinterpret_cast<const float4 *>(stg + r * 80 + seg * 16);
+        if (wrow0 + r < M) {
+          float *dst = ob + (size_t)(wrow0 + r) * ldo + col0 + hh * 16 + seg * 4;
+          if (RED) red_add_v4(dst, w.x, w.y, w.z, w.w);
+          else *reinterpret_cast<float4 *>(dst) = w;
+        }
+      }
+      __syncwarp();
+    }
+  } else if (row < M) {
+    float *o = ob + (size_t)row * ldo + col0;
+    const float *r = res ? res + (size_t)row * ldo + col0 : nullptr;
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (col0 + i < N) {
+        if (RED) atomicAdd(o + i, v[i]);
+        else o[i] = v[i] + (r ? r[i] : 0.f);
+      }
+  }
+}
+__device__ __forceinline__ void store_chunk_bf16(const float (&v)[32], __nv_bfloat16 *ob, int ldo, const __nv_bfloat16 *res,
+                                                 int M, int N, int row, int wrow0, int col0, uint8_t *stg, int lane) {
+  const bool vec_ok = col0 + 32 <= N && res == nullptr && (reinterpret_cast<uintptr_t>(ob) & 15) == 0 && (ldo & 7) == 0 &&
+                      (col0 & 7) == 0;
+  if (vec_ok) {
+    const int sr = lane >> 2, seg = lane & 3;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      *reinterpret_cast<uint4 *>(stg + lane * 80 + k * 16) =
+          make_uint4(pack_bf16(v[8 * k], v[8 * k + 1]), pack_bf16(v[8 * k + 2], v[8 * k + 3]),
+                     pack_bf16(v[8 * k + 4], v[8 * k + 5]), pack_bf16(v[8 * k + 6], v[8 * k + 7]));
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int r = it * 8 + sr;
+      const uint4 w = *reinterpret_cast<const uint4 *>(stg + r * 80 + seg * 16);
+      if (wrow0 + r < M) *reinterpret_cast<uint4 *>(ob + (size_t)(wrow0 + r) * ldo + col0 + seg * 8) = w;
+    }
+    __syncwarp();
+  } else if (row < M) {
+    __nv_bfloat16 *o = ob + (size_t)row * ldo + col0;
+    const __nv_bfloat16 *r = res ? res + (size_t)row * ldo + col0 : nullptr;
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (col0 + i < N) o[i] = __float2bfloat16_rn(v[i] + (r ? __bfloat162float(r[i]) : 0.f));
+  }
+}
+
+template <int BN, int EPI>
 __global__ void __launch_bounds__(320, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GemmArgs g) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int A_STAGE = BM * BK * 2, B_STAGE = BN * BK * 2;
+  constexpr uint32_t ACC_COLS = 2 * BN;                       // bias-gradient accumulators (WGRAD) live behind these
+  constexpr uint32_t TMEM_COLS = (EPI == EPI_WGRAD ? ACC_COLS + 64 : ACC_COLS) <= 128 ? 128
+                                 : (EPI == EPI_WGRAD ? ACC_COLS + 64 : ACC_COLS) <= 256 ? 256 : 512;
+  static_assert((EPI == EPI_WGRAD ? ACC_COLS + 64 : ACC_COLS) <= 512, "TMEM budget");
   uint8_t *sA = smem;
   uint8_t *sB = smem + STAGES * A_STAGE;
-  uint64_t *full = reinterpret_cast<uint64_t *>(smem + STAGES * (A_STAGE + B_STAGE));
+  uint8_t *sOnes = sB + STAGES * B_STAGE;                      // [16][64] bf16 ones (2 KB), WGRAD bias-gradient operand
+  uint64_t *full = reinterpret_cast<uint64_t *>(sOnes + 2048);
   uint64_t *empty = full + STAGES;
   uint64_t *acc_full = empty + STAGES;   // [2]
   uint64_t *acc_empty = acc_full + 2;    // [2]
@@ -73,6 +192,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
   const int tiles_m = (g.M + BM - 1) / BM, tiles_n = (g.N + BN - 1) / BN;
   const int n_tiles = tiles_m * tiles_n;
   const int k_steps = (g.K + BK - 1) / BK;
+  const int kps = (k_steps + g.splits - 1) / g.splits;   // K steps per split (host guarantees every split is non-empty)
+  const int n_items = n_tiles * g.splits;                // work list: item i = (tile i % n_tiles, split i / n_tiles)
+  const bool with_bias_grad = EPI == EPI_WGRAD && g.bias_grad != nullptr;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -85,7 +207,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     }
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc<2 * BN>(tmem_slot);
+  if (EPI == EPI_WGRAD) {
+    for (int i = threadIdx.x; i < 512; i += 320) reinterpret_cast<uint32_t *>(sOnes)[i] = 0x3F803F80u;  // bf16 1.0 pairs
+    fence_proxy_async_smem();
+  }
+  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -95,9 +221,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     // ------------------------------- TMA producer -------------------------------
     if (lane == 0) {
       uint32_t it = 0;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int t = item % n_tiles, sp = item / n_tiles;
         const int m0 = (t % tiles_m) * BM, n0 = (t / tiles_m) * BN;
-        for (int ks = 0; ks < k_steps; ++ks, ++it) {
+        const int ks0 = sp * kps, ks1 = min(k_steps, ks0 + kps);
+        for (int ks = ks0; ks < ks1; ++ks, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1u;
           mbar_wait(empty + s, ph ^ 1u);  // slot free (first pass returns immediately)
@@ -122,20 +250,29 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     // ------------------------------- MMA issuer -------------------------------
     if (lane == 0) {
       const uint32_t IDESC = make_idesc_bf16(BM, BN) | (g.a_mn ? 1u << 15 : 0u) | (g.b_mn ? 1u << 16 : 0u);
+      const uint32_t IDESC_ONES = make_idesc_bf16(BM, 16) | (g.a_mn ? 1u << 15 : 0u);   // B = K-major tile of ones
+      const uint64_t ones_desc = make_desc_sw128(smem_u32(sOnes));
       uint32_t it = 0, tl = 0;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tl) {
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++tl) {
+        const int t = item % n_tiles, sp = item / n_tiles;
+        const bool bias_tile = with_bias_grad && (t / tiles_m) == 0;
+        const int ks0 = sp * kps, ks1 = min(k_steps, ks0 + kps);
         const int b = tl & 1;
         mbar_wait(acc_empty + b, ((tl >> 1) & 1u) ^ 1u);  // epilogue drained this accumulator
         fence_after_sync();
-        for (int ks = 0; ks < k_steps; ++ks, ++it) {
+        for (int ks = ks0; ks < ks1; ++ks, ++it) {
           const int s = it % STAGES;
           mbar_wait(full + s, (it / STAGES) & 1u);
           fence_after_sync();
           const uint32_t a0 = smem_u32(sA + s * A_STAGE), b0 = smem_u32(sB + s * B_STAGE);
 #pragma unroll
-          for (int kk = 0; kk < BK / 16; ++kk)
-            mma_bf16(tmem + b * BN, g.a_mn ? make_desc_sw128_mn(a0 + kk * 2048) : make_desc_sw128(a0 + kk * 32),
-                     g.b_mn ? make_desc_sw128_mn(b0 + kk * 2048) : make_desc_sw128(b0 + kk * 32), IDESC, (ks | kk) != 0);
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            const uint64_t adesc = g.a_mn ? make_desc_sw128_mn(a0 + kk * 2048) : make_desc_sw128(a0 + kk * 32);
+            mma_bf16(tmem + b * BN, adesc, g.b_mn ? make_desc_sw128_mn(b0 + kk * 2048) : make_desc_sw128(b0 + kk * 32), IDESC,
+                     (ks != ks0) || kk != 0);
+            if (EPI == EPI_WGRAD && bias_tile)
+              mma_bf16(tmem + ACC_COLS + b * 32, adesc, ones_desc, IDESC_ONES, (ks != ks0) || kk != 0);
+          }
           mma_commit(empty + s);  // frees the smem slot when these MMAs retire
         }
         mma_commit(acc_full + b);
@@ -150,14 +287,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     const int et = threadIdx.x - 64;    // 0..255
     const int row_in_tile = q * 32 + lane;
     constexpr int NCHUNK = BN / 64;     // 32-column chunks per warp
+    uint8_t *stg = reinterpret_cast<uint8_t *>(stage) + (warp - 2) * STG_BYTES;
+    const unsigned long long seed = (EPI != EPI_WGRAD && g.t16) ? attn::effective_seed(g.seed, g.seed_offset) : 0ull;
     uint32_t tl = 0;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tl) {
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++tl) {
+      const int t = item % n_tiles;
       const int b = tl & 1;
       const int m0 = (t % tiles_m) * BM, n0 = (t / tiles_m) * BN;
       const int row = m0 + row_in_tile;
+      const int wrow0 = m0 + q * 32;  // first accumulator row of this warp
       float *sb = sbias + b * BN;
-      if (et < BN) sb[et] = (g.bias != nullptr && n0 + et < g.N) ? __ldg(g.bias + n0 + et) : 0.f;
-      asm volatile("bar.sync 1, 256;" ::: "memory");  // bias visible; everybody is done with the tile before last
+      if (EPI == EPI_FWD) {
+        if (et < BN) sb[et] = (g.bias != nullptr && n0 + et < g.N) ? __ldg(g.bias + n0 + et) : 0.f;
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // bias visible; everybody is done with the tile before last
+      }
+      uint32_t rk = 0;
+      if (EPI != EPI_WGRAD && g.t16) rk = attn::drop_row_key(seed, (unsigned long long)row);
       mbar_wait(acc_full + b, (tl >> 1) & 1u);
       fence_after_sync();
       const uint32_t taddr = tmem + b * BN + half * (BN / 2) + ((uint32_t)(q * 32) << 16);
@@ -171,106 +316,116 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         const int c0 = half * (BN / 2) + ci * 32;
         const int col0 = n0 + c0;
         if (col0 < g.N) {
-        float v[32];
-        const float4 *b4 = reinterpret_cast<const float4 *>(sb + c0);
+          float v[32];
+          if (EPI == EPI_FWD) {
+            const float4 *b4 = reinterpret_cast<const float4 *>(sb + c0);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 bb = b4[i];
-          v[4 * i] = __uint_as_float(cur[4 * i]) + bb.x;
-          v[4 * i + 1] = __uint_as_float(cur[4 * i + 1]) + bb.y;
-          v[4 * i + 2] = __uint_as_float(cur[4 * i + 2]) + bb.z;
-          v[4 * i + 3] = __uint_as_float(cur[4 * i + 3]) + bb.w;
-        }
-        if (g.act == 1) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-        } else if (g.act == 2) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
-        }
-        if (g.rowmax == 16) {
-          // max over the 16 rows of each half-warp (16 consecutive rows = the 16 points of one cloud): 16 columns at a
-          // time go through a per-warp [32][17] transpose scratch; lanes 0-15 reduce rows 0-15, lanes 16-31 rows 16-31
-          float *tp = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(stage) + (warp - 2) * STG_BYTES);
-          const int l16 = lane & 15, grp = lane >> 4;
-          const int wrow0 = m0 + q * 32;  // first accumulator row of this warp
-#pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) tp[lane * 17 + i] = row < g.M ? v[hh * 16 + i] : -INFINITY;
-            __syncwarp();
-            float mx = -INFINITY;
-#pragma unroll
-            for (int r2 = 0; r2 < 16; ++r2) mx = fmaxf(mx, tp[(grp * 16 + r2) * 17 + l16]);
-            __syncwarp();
-            const int col = col0 + hh * 16 + l16;
-            if (col < g.N && wrow0 + grp * 16 < g.M) {
-              const size_t orow = (size_t)(wrow0 >> 4) + grp;
-              if (g.out_f32) reinterpret_cast<float *>(g.out)[orow * g.ldo + col] = mx;
-              else reinterpret_cast<__nv_bfloat16 *>(g.out)[orow * g.ldo + col] = __float2bfloat16_rn(mx);
+            for (int i = 0; i < 8; ++i) {
+              const float4 bb = b4[i];
+              v[4 * i] = __uint_as_float(cur[4 * i]) + bb.x;
+              v[4 * i + 1] = __uint_as_float(cur[4 * i + 1]) + bb.y;
+              v[4 * i + 2] = __uint_as_float(cur[4 * i + 2]) + bb.z;
+              v[4 * i + 3] = __uint_as_float(cur[4 * i + 3]) + bb.w;
             }
-          }
-        } else {
-          // Coalesced stores: the warp's 32 x 32 chunk goes through a per-warp [32][80 B] staging buffer (one row per
-          // lane in, 8 rows x 64 B per store instruction out), so a store instruction touches 8 lines instead of 32.
-          const bool full32 = col0 + 32 <= g.N;
-          uint8_t *stg = reinterpret_cast<uint8_t *>(stage) + (warp - 2) * STG_BYTES;
-          const int wrow0 = m0 + q * 32;
-          const int sr = lane >> 2, seg = lane & 3;
-          const bool vec_ok = full32 && g.residual == nullptr && (reinterpret_cast<uintptr_t>(g.out) & 15) == 0;
-          if (g.out_f32) {
-            float *ob = reinterpret_cast<float *>(g.out);
-            if (vec_ok && (g.ldo & 3) == 0 && (col0 & 3) == 0) {
+            if (g.out2 != nullptr)
+              store_chunk_bf16(v, reinterpret_cast<__nv_bfloat16 *>(g.out2), g.ldo, nullptr, g.M, g.N, row, wrow0, col0, stg, lane);
+            if (g.act == 1) {
 #pragma unroll
-              for (int hh = 0; hh < 2; ++hh) {
+              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+            } else if (g.act == 2) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  *reinterpret_cast<float4 *>(stg + lane * 80 + k * 16) =
-                      make_float4(v[hh * 16 + 4 * k], v[hh * 16 + 4 * k + 1], v[hh * 16 + 4 * k + 2], v[hh * 16 + 4 * k + 3]);
-                __syncwarp();
+              for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+            }
+            if (g.t16) {
 #pragma unroll
-                for (int it = 0; it < 4; ++it) {
-                  const int r = it * 8 + sr;
-                  const float4 w = *reinterpret_cast<const float4 *>(stg + r * 80 + seg * 16);
-                  if (wrow0 + r < g.M)
-                    *reinterpret_cast<float4 *>(ob + (size_t)(wrow0 + r) * g.ldo + col0 + hh * 16 + seg * 4) = w;
-                }
-                __syncwarp();
+              for (int i = 0; i < 32; i += 2) {
+                const uint32_t hh = attn::drop_pair_hash(rk, (uint32_t)(col0 + i) >> 1);
+                v[i] = (hh & 0xFFFFu) >= g.t16 ? v[i] * g.inv_keep : 0.f;
+                v[i + 1] = (hh >> 16) >= g.t16 ? v[i + 1] * g.inv_keep : 0.f;
               }
-            } else if (row < g.M) {
-              float *o = ob + (size_t)row * g.ldo + col0;
-              const float *r = g.residual ? reinterpret_cast<const float *>(g.residual) + (size_t)row * g.ldo + col0 : nullptr;
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (col0 + i < g.N) o[i] = v[i] + (r ? r[i] : 0.f);
             }
           } else {
-            __nv_bfloat16 *ob = reinterpret_cast<__nv_bfloat16 *>(g.out);
-            if (vec_ok && (g.ldo & 7) == 0 && (col0 & 7) == 0) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                *reinterpret_cast<uint4 *>(stg + lane * 80 + k * 16) =
-                    make_uint4(pack_bf16(v[8 * k], v[8 * k + 1]), pack_bf16(v[8 * k + 2], v[8 * k + 3]),
-                               pack_bf16(v[8 * k + 4], v[8 * k + 5]), pack_bf16(v[8 * k + 6], v[8 * k + 7]));
-              __syncwarp();
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(cur[i]);
+          }
+          if (EPI == EPI_DGRAD && g.act != 0 && row < g.M) {
+            // multiply by the activation (+ dropout) derivative read from the saved forward tensor
+            const __nv_bfloat16 *ax = reinterpret_cast<const __nv_bfloat16 *>(g.aux) + (size_t)row * g.ld_aux + col0;
+            const bool vec = col0 + 32 <= g.N && (g.ld_aux & 7) == 0 && (reinterpret_cast<uintptr_t>(g.aux) & 15) == 0;
 #pragma unroll
-              for (int it = 0; it < 4; ++it) {
-                const int r = it * 8 + sr;
-                const uint4 w = *reinterpret_cast<const uint4 *>(stg + r * 80 + seg * 16);
-                if (wrow0 + r < g.M) *reinterpret_cast<uint4 *>(ob + (size_t)(wrow0 + r) * g.ldo + col0 + seg * 8) = w;
+            for (int k = 0; k < 4; ++k) {
+              float a8[8];
+              if (vec) {
+                const uint4 w = __ldg(reinterpret_cast<const uint4 *>(ax) + k);
+                const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  a8[2 * e] = __uint_as_float(ww[e] << 16);
+                  a8[2 * e + 1] = __uint_as_float(ww[e] & 0xFFFF0000u);
+                }
+              } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) a8[e] = col0 + k * 8 + e < g.N ? __bfloat162float(ax[k * 8 + e]) : 0.f;
               }
-              __syncwarp();
-            } else if (row < g.M) {
-              __nv_bfloat16 *o = ob + (size_t)row * g.ldo + col0;
-              const __nv_bfloat16 *r =
-                  g.residual ? reinterpret_cast<const __nv_bfloat16 *>(g.residual) + (size_t)row * g.ldo + col0 : nullptr;
+              if (g.act == 1) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (col0 + i < g.N) o[i] = __float2bfloat16_rn(v[i] + (r ? __bfloat162float(r[i]) : 0.f));
+                for (int e = 0; e < 8; ++e) v[k * 8 + e] = a8[e] > 0.f ? v[k * 8 + e] * g.inv_keep : 0.f;
+              } else {
+#pragma unroll
+                for (int e = 0; e < 8; e += 2) {
+                  float m0_ = 1.f, m1_ = 1.f;
+                  if (g.t16) {
+                    const uint32_t hh = attn::drop_pair_hash(rk, (uint32_t)(col0 + k * 8 + e) >> 1);
+                    m0_ = (hh & 0xFFFFu) >= g.t16 ? g.inv_keep : 0.f;
+                    m1_ = (hh >> 16) >= g.t16 ? g.inv_keep : 0.f;
+                  }
+                  v[k * 8 + e] *= gelu_grad(a8[e]) * m0_;
+                  v[k * 8 + e + 1] *= gelu_grad(a8[e + 1]) * m1_;
+                }
+              }
             }
           }
+          if (EPI == EPI_FWD && g.rowmax == 16) {
+            // max over the 16 rows of each half-warp (16 consecutive rows = the 16 points of one cloud): 16 columns at a
+            // time go through a per-warp [32][17] transpose scratch; lanes 0-15 reduce rows 0-15, lanes 16-31 rows 16-31
+            float *tp = reinterpret_cast<float *>(stg);
+            const int l16 = lane & 15, grp = lane >> 4;
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) tp[lane * 17 + i] = row < g.M ? v[hh * 16 + i] : -INFINITY;
+              __syncwarp();
+              float mx = -INFINITY;
+#pragma unroll
+              for (int r2 = 0; r2 < 16; ++r2) mx = fmaxf(mx, tp[(grp * 16 + r2) * 17 + l16]);
+              __syncwarp();
+              const int col = col0 + hh * 16 + l16;
+              if (col < g.N && wrow0 + grp * 16 < g.M) {
+                const size_t orow = (size_t)(wrow0 >> 4) + grp;
+                if (g.out_f32) reinterpret_cast<float *>(g.out)[orow * g.ldo + col] = mx;
+                else reinterpret_cast<__nv_bfloat16 *>(g.out)[orow * g.ldo + col] = __float2bfloat16_rn(mx);
+              }
+            }
+          } else if (EPI == EPI_WGRAD) {
+            if (g.red_out)
+              store_chunk_f32<true>(v, reinterpret_cast<float *>(g.out), g.ldo, nullptr, g.M, g.N, row, wrow0, col0, stg, lane);
+            else
+              store_chunk_f32<false>(v, reinterpret_cast<float *>(g.out), g.ldo, nullptr, g.M, g.N, row, wrow0, col0, stg, lane);
+          } else if (g.out_f32) {
+            store_chunk_f32<false>(v, reinterpret_cast<float *>(g.out), g.ldo, reinterpret_cast<const float *>(g.residual), g.M,
+                                   g.N, row, wrow0, col0, stg, lane);
+          } else {
+            store_chunk_bf16(v, reinterpret_cast<__nv_bfloat16 *>(g.out), g.ldo,
+                             reinterpret_cast<const __nv_bfloat16 *>(g.residual), g.M, g.N, row, wrow0, col0, stg, lane);
+          }
         }
-        }
+      }
+      if (EPI == EPI_WGRAD && with_bias_grad && n0 == 0 && half == 0) {
+        // every column of the N = 16 ones-product equals sum_k A[row][k]: the bias gradient of output feature `row`
+        uint32_t r16[16];
+        attn::tmem_ld16_async(tmem + ACC_COLS + b * 32 + ((uint32_t)(q * 32) << 16), r16);
+        attn::tmem_wait16(r16);
+        if (row < g.M) atomicAdd(g.bias_grad + row, __uint_as_float(r16[0]));
       }
       fence_before_sync();
       mbar_arrive(acc_empty + b);
@@ -278,24 +433,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<2 * BN>(tmem);
+  if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem);
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void *p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
+using attn::EncodeTiledFn;
+using attn::encode_fn;
 
 // row-major [rows, K] bf16 with leading dimension ld (elements); box = [box_rows x 64 elements], 128-byte swizzle
 int make_map(CUtensorMap *map, const void *ptr, int rows, int K, int ld, int box_rows) {
@@ -325,26 +467,116 @@ int make_map_mn(CUtensorMap *map, const void *ptr, int rows, int K, int ld) {
   return r == CUDA_SUCCESS ? SV_OK : SV_ERR_INVALID_ARG;
 }
 
-template <int BN>
-int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mb, const GemmArgs &g, cudaStream_t st) {
-  constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + (2 * STAGES + 4) * 8 + 16 + 8 * STG_BYTES + 2 * BN * 4;
-  auto kern = gemm_kernel<BN>;
-  static int sms_of_dev[64] = {0};  // also marks "attribute set on this device" (one-time host work per device)
+int device_sms(int *dev_out) {
+  static int sms_of_dev[64] = {0};
   int dev = 0;
   cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64) return SV_ERR_INVALID_ARG;
+  if (dev < 0 || dev >= 64) return 0;
   if (sms_of_dev[dev] == 0) {
-    int rc = sv::cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (rc) return rc;
     int n = 148;
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     sms_of_dev[dev] = n;
   }
-  const int sms = sms_of_dev[dev];
-  const int tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN);
-  const int grid = tiles < sms ? tiles : sms;
+  *dev_out = dev;
+  return sms_of_dev[dev];
+}
+
+template <int BN, int EPI>
+int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mb, const GemmArgs &g, cudaStream_t st) {
+  constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 2048 + (2 * STAGES + 4) * 8 + 16 + 8 * STG_BYTES + 2 * BN * 4;
+  auto kern = gemm_kernel<BN, EPI>;
+  static bool configured[64] = {false};
+  int dev = 0;
+  const int sms = device_sms(&dev);
+  if (sms == 0) return SV_ERR_INVALID_ARG;
+  if (!configured[dev]) {
+    int rc = sv::cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (rc) return rc;
+    configured[dev] = true;
+  }
+  const int items = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN) * g.splits;
+  const int grid = items < sms ? items : sms;
   kern<<<grid, 320, smem, st>>>(ma, mb, g);
   return sv::after_launch();
+}
+
+// Tile width: the persistent grid runs ceil(tiles / SMs) waves, so the cheapest width is the one whose LAST wave is
+// fullest; relative cost of one tile by width (MMA time + the fixed per-tile overhead; narrow tiles are shared-memory
+// operand-bandwidth bound) measured on the B200.
+int pick_bn(int M, int N, int sms, bool allow256) {
+  const int cand[4] = {256, 192, 128, 64};
+  const float w[4] = {1.00f, 0.78f, 0.56f, 0.34f};
+  int best = 64;
+  float best_cost = 1e30f;
+  const int tm = (M + BM - 1) / BM;
+  for (int i = 0; i < 4; ++i) {
+    if (cand[i] == 256 && !allow256) continue;
+    const int tiles = tm * ((N + cand[i] - 1) / cand[i]);
+    const float cost = (float)((tiles + sms - 1) / sms) * w[i];
+    if (cost < best_cost - 1e-6f) {
+      best_cost = cost;
+      best = cand[i];
+    }
+  }
+  return best;
+}
+
+template <int EPI>
+int dispatch(int bn, const CUtensorMap &ma, const CUtensorMap &mb, const GemmArgs &g, cudaStream_t st) {
+  if (bn == 256) {
+    if constexpr (EPI == EPI_WGRAD) return SV_ERR_INVALID_ARG;   // 2 x 256 accumulator columns leave no room for the bias sums
+    else return launch_gemm<256, EPI>(ma, mb, g, st);
+  }
+  if (bn == 192) return launch_gemm<192, EPI>(ma, mb, g, st);
+  if (bn == 128) return launch_gemm<128, EPI>(ma, mb, g, st);
+  return launch_gemm<64, EPI>(ma, mb, g, st);
+}
+
+int run_gemm(int epi, const void *A, int lda, int a_t, const void *B, int ldb, int b_t, GemmArgs &g, cudaStream_t st) {
+  const int M = g.M, N = g.N, K = g.K;
+  if (M < 0 || N < 0 || K < 0) return SV_ERR_INVALID_ARG;
+  if (M == 0 || N == 0) return SV_OK;
+  if (!A || !B || !g.out || K < 1 || (lda % 8) || (ldb % 8)) return SV_ERR_INVALID_ARG;
+  if (a_t ? lda < M : (lda < K || (K % 8))) return SV_ERR_INVALID_ARG;
+  if (b_t ? ldb < N : (ldb < K || (K % 8))) return SV_ERR_INVALID_ARG;
+  if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) return SV_ERR_INVALID_ARG;
+  int dev = 0;
+  const int sms = device_sms(&dev);
+  if (sms == 0) return SV_ERR_INVALID_ARG;
+  g.a_mn = a_t ? 1 : 0;
+  g.b_mn = b_t ? 1 : 0;
+  const int bn = pick_bn(M, N, sms, epi != EPI_WGRAD);
+  g.splits = 1;
+  if (epi == EPI_WGRAD && g.red_out) {
+    // split-K: the output of a weight gradient is small (a few dozen tiles), the contraction runs over every token
+    const int tiles = ((M + BM - 1) / BM) * ((N + bn - 1) / bn), k_steps = (K + BK - 1) / BK;
+    float best_eff = 0.f;
+    for (int s = 1; s <= 16 && s * 4 <= k_steps; ++s) {
+      const int kps = (k_steps + s - 1) / s;
+      if ((s - 1) * kps >= k_steps) continue;  // an empty split
+      const int items = tiles * s;
+      const float eff = (float)items / (float)(((items + sms - 1) / sms) * sms) - 0.01f * s;
+      if (eff > best_eff) {
+        best_eff = eff;
+        g.splits = s;
+      }
+    }
+  }
+  CUtensorMap ma, mb;
+  int rc = a_t ? make_map_mn(&ma, A, M, K, lda) : make_map(&ma, A, M, K, lda, BM);
+  if (rc) return rc;
+  rc = b_t ? make_map_mn(&mb, B, N, K, ldb) : make_map(&mb, B, N, K, ldb, bn);
+  if (rc) return rc;
+  if (epi == EPI_FWD) return dispatch<EPI_FWD>(bn, ma, mb, g, st);
+  if (epi == EPI_DGRAD) return dispatch<EPI_DGRAD>(bn, ma, mb, g, st);
+  return dispatch<EPI_WGRAD>(bn, ma, mb, g, st);
+}
+
+void set_dropout(GemmArgs &g, float p, unsigned long long seed) {
+  g.t16 = attn::drop_threshold(p);
+  g.inv_keep = 1.0f / (1.0f - p);
+  g.seed = seed;
+  g.seed_offset = sv::g_seed_offset;
 }
 
 }  // namespace
@@ -357,23 +589,53 @@ extern "C" int sv_gemm_bf16(const void *A, int lda, const void *B, int ldb, int 
 extern "C" int sv_gemm_bf16_ex(const void *A, int lda, int a_transposed, const void *B, int ldb, int b_transposed, int M,
                                int N, int K, const float *bias, int act, const void *residual, void *out, int ldo,
                                int out_f32, int rowmax, void *stream) {
-  if (M < 0 || N < 0 || K < 0) return SV_ERR_INVALID_ARG;
-  if (M == 0 || N == 0) return SV_OK;
-  if (!A || !B || !out || K < 8 || (lda % 8) || (ldb % 8)) return SV_ERR_INVALID_ARG;
-  if (a_transposed ? lda < M : (lda < K || (K % 8))) return SV_ERR_INVALID_ARG;
-  if (b_transposed ? ldb < N : (ldb < K || (K % 8))) return SV_ERR_INVALID_ARG;
-  if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) return SV_ERR_INVALID_ARG;
   if (act < 0 || act > 2 || (rowmax != 0 && rowmax != 16) || (rowmax && residual)) return SV_ERR_INVALID_ARG;
   if (rowmax && (M % 16)) return SV_ERR_INVALID_ARG;
-  GemmArgs g{M, N, K, bias, residual, out, act, out_f32, rowmax, ldo, a_transposed ? 1 : 0, b_transposed ? 1 : 0};
-  CUtensorMap ma, mb;
-  const int bn = N > 128 ? 256 : (N > 64 ? 128 : 64);
-  int rc = a_transposed ? make_map_mn(&ma, A, M, K, lda) : make_map(&ma, A, M, K, lda, BM);
-  if (rc) return rc;
-  rc = b_transposed ? make_map_mn(&mb, B, N, K, ldb) : make_map(&mb, B, N, K, ldb, bn);
-  if (rc) return rc;
+  GemmArgs g{};
+  g.M = M; g.N = N; g.K = K; g.bias = bias; g.residual = residual; g.out = out; g.act = act; g.out_f32 = out_f32;
+  g.rowmax = rowmax; g.ldo = ldo; g.inv_keep = 1.f;
+  return run_gemm(EPI_FWD, A, lda, a_transposed, B, ldb, b_transposed, g, (cudaStream_t)stream);
+}
+
+extern "C" int sv_linear_fwd_bf16(const void *x, int ldx, const void *w, int ldw, int M, int N, int K, const float *bias,
+                                  int act, float dropout_p, unsigned long long seed, void *out, int ldo, int out_f32,
+                                  void *pre_out, void *stream) {
+  if (act < 0 || act > 2 || !(dropout_p >= 0.f) || dropout_p >= 1.f) return SV_ERR_INVALID_ARG;
+  GemmArgs g{};
+  g.M = M; g.N = N; g.K = K; g.bias = bias; g.out = out; g.act = act; g.out_f32 = out_f32; g.ldo = ldo; g.out2 = pre_out;
+  set_dropout(g, dropout_p, seed);
+  return run_gemm(EPI_FWD, x, ldx, 0, w, ldw, 0, g, (cudaStream_t)stream);
+}
+
+extern "C" int sv_linear_dgrad_bf16(const void *gy, int ldg, const void *w, int ldw, int M, int N, int Kin, int dact,
+                                    const void *aux, int ld_aux, float dropout_p, unsigned long long seed, void *dx, int ldx,
+                                    int out_f32, void *stream) {
+  // dx[M,Kin] = gy[M,N] . w[N,Kin]: contraction over N, the weight is the transposed (MN-major) B operand
+  if (dact < 0 || dact > 2 || (dact && !aux) || !(dropout_p >= 0.f) || dropout_p >= 1.f) return SV_ERR_INVALID_ARG;
+  GemmArgs g{};
+  g.M = M; g.N = Kin; g.K = N; g.out = dx; g.act = dact; g.out_f32 = out_f32; g.ldo = ldx; g.aux = aux; g.ld_aux = ld_aux;
+  set_dropout(g, dropout_p, seed);
+  return run_gemm(EPI_DGRAD, gy, ldg, 0, w, ldw, 1, g, (cudaStream_t)stream);
+}
+
+extern "C" int sv_linear_wgrad_bf16(const void *gy, int ldg, const void *x, int ldx, int M, int N, int Kin, float *dw,
+                                    int ld_dw, float *db, int accumulate, void *stream) {
+  // dw[N,Kin] (+)= gy[M,N]^T . x[M,Kin]: contraction over the M tokens, both operands transposed in memory; db[N] (+)= column
+  // sums of gy.  accumulate = 0: dw / db are overwritten (zero-filled here first, then reduced into by the split-K work list)
+  if (M < 0 || N < 0 || Kin < 0) return SV_ERR_INVALID_ARG;
+  if (N == 0 || Kin == 0) return SV_OK;
+  if (!dw) return SV_ERR_INVALID_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  if (bn == 256) return launch_gemm<256>(ma, mb, g, st);
-  if (bn == 128) return launch_gemm<128>(ma, mb, g, st);
-  return launch_gemm<64>(ma, mb, g, st);
+  if (!accumulate) {
+    int rc = sv::cuda_status(cudaMemsetAsync(dw, 0, (size_t)N * ld_dw * sizeof(float), st));
+    if (rc) return rc;
+    if (db) {
+      rc = sv::cuda_status(cudaMemsetAsync(db, 0, (size_t)N * sizeof(float), st));
+      if (rc) return rc;
+    }
+  }
+  if (M == 0) return SV_OK;
+  GemmArgs g{};
+  g.M = N; g.N = Kin; g.K = M; g.out = dw; g.out_f32 = 1; g.ldo = ld_dw; g.red_out = 1; g.bias_grad = db; g.inv_keep = 1.f;
+  return run_gemm(EPI_WGRAD, gy, ldg, 1, x, ldx, 1, g, st);
 }

@@ -65,6 +65,14 @@ def _bert_self_attention_forward(self, hidden_states, attention_mask=None, past_
     return out, None
 
 
+def _bert_feed_forward_chunk(self, attention_output):
+    """BertLayer.feed_forward_chunk (BertIntermediate: dense + gelu; BertOutput: dense, dropout, LayerNorm(+ residual)) as
+    one ops.ffn (two native GEMMs, gelu in the first epilogue) + the fused dropout / residual / LayerNorm kernel."""
+    inter, out = self.intermediate.dense, self.output
+    h = ops.ffn(attention_output, inter.weight, inter.bias, out.dense.weight, out.dense.bias, activation="gelu")
+    return out.LayerNorm(h, residual=attention_output, dropout_p=out.dropout.p if self.training else 0.0)
+
+
 def _fuse_bert_layer_norms(bert):
     """Same modules, parameters and state_dict keys as the HF model; only the forward of the LayerNorms, of the two
     residual tails of every block (-> ops.layer_norm) and of the self-attention core (-> ops.attention) is re-routed."""
@@ -76,6 +84,8 @@ def _fuse_bert_layer_norms(bert):
     for layer in bert.encoder.layer:
         for tail in (layer.attention.output, layer.output):
             tail.forward = types.MethodType(_bert_output_forward, tail)
+        if getattr(bert.config, "hidden_act", "gelu") == "gelu" and getattr(layer, "chunk_size_feed_forward", 0) == 0:
+            layer.feed_forward_chunk = types.MethodType(_bert_feed_forward_chunk, layer)
         if layer.attention.self.attention_head_size == 64:
             layer.attention.self.forward = types.MethodType(_bert_self_attention_forward, layer.attention.self)
 

@@ -153,8 +153,8 @@ class TransformerEncoderLayer(nn.Module):
         self.prenorm = prenorm
 
     def _ffn(self, x):
-        h = ops.linear(x, self.linear1.weight, self.linear1.bias, activation=self.activation_name)
-        return ops.linear(self.dropout(h), self.linear2.weight, self.linear2.bias)
+        return ops.ffn(x, self.linear1.weight, self.linear1.bias, self.linear2.weight, self.linear2.bias,
+                       activation=self.activation_name, dropout_p=self.dropout.p if self.training else 0.0)
 
     def forward(self, tgt, tgt_mask=None, tgt_key_padding_mask=None):
         tgt2 = self.norm1(tgt) if self.prenorm else tgt
@@ -215,8 +215,9 @@ class TransformerDecoderLayer(nn.Module):
         tgt = tgt + self.dropout1(tgt2)
         tgt2, ca = self.multihead_attn(self.norm2(tgt), memory, memory, key_padding_mask=memory_key_padding_mask)
         tgt = tgt + self.dropout2(tgt2)
-        h = ops.linear(self.norm3(tgt), self.linear1.weight, self.linear1.bias, activation=self.activation_name)
-        tgt = tgt + self.dropout3(ops.linear(self.dropout(h), self.linear2.weight, self.linear2.bias))
+        tgt = tgt + self.dropout3(ops.ffn(self.norm3(tgt), self.linear1.weight, self.linear1.bias, self.linear2.weight,
+                                          self.linear2.bias, activation=self.activation_name,
+                                          dropout_p=self.dropout.p if self.training else 0.0))
         return tgt, sa, ca
 
 

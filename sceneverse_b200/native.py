@@ -120,3 +120,104 @@ def gemm_ex(a, b, a_transposed=False, b_transposed=False, bias=None, act=None, o
                                  torch.cuda.current_stream(a.device).cuda_stream)
     _lib.check(lib, st, "sv_gemm_bf16_ex")
     return out
+
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _rows_ok(t):
+    return t.dim() == 2 and t.stride(1) == 1 and t.stride(0) % 8 == 0 and t.data_ptr() % 16 == 0
+
+
+def linear_fwd(x, w, bias=None, act=None, dropout_p=0.0, seed=0, out_dtype=torch.bfloat16, want_pre=False, n_out=None,
+               out=None):
+    """out = dropout(act(x @ w[:n].T + bias)): x (M,K) bf16, w (N,K) bf16, bias (N) f32.  `out` may be a wider buffer
+    (M, Np >= N): only the first N columns are written.  want_pre: also return the pre-activation (bf16, same layout)."""
+    assert x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and _rows_ok(x) and _rows_ok(w), (x.shape, x.stride(), w.shape)
+    M, K = x.shape
+    N = w.shape[0] if n_out is None else n_out
+    if out is None:
+        out = torch.empty((M, N), dtype=out_dtype, device=x.device)
+    pre = torch.empty_like(out) if want_pre else None
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.is_contiguous()
+    lib = _lib.gps()
+    with torch.cuda.device(x.device):
+        st = lib.sv_linear_fwd_bf16(x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), M, N, K,
+                                    bias.data_ptr() if bias is not None else None, _ACT[act], float(dropout_p), int(seed),
+                                    out.data_ptr(), out.stride(0), 1 if out.dtype == torch.float32 else 0,
+                                    pre.data_ptr() if pre is not None else None, _stream(x))
+    _lib.check(lib, st, "sv_linear_fwd_bf16")
+    return (out, pre) if want_pre else out
+
+
+def linear_dgrad(g, w, act=None, aux=None, dropout_p=0.0, seed=0, n_red=None, out_dtype=torch.bfloat16):
+    """dx (M,Kin) = (g (M,N) @ w (N,Kin)) * act'(aux) [* dropout mask]; n_red > w.shape[0]: g carries zero pad columns."""
+    assert g.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and _rows_ok(g) and _rows_ok(w)
+    M = g.shape[0]
+    N = g.shape[1] if n_red is None else n_red
+    Kin = w.shape[1]
+    dx = torch.empty((M, Kin), dtype=out_dtype, device=g.device)
+    if aux is not None:
+        assert aux.dtype == torch.bfloat16 and aux.shape == (M, Kin) and aux.stride(1) == 1
+    lib = _lib.gps()
+    with torch.cuda.device(g.device):
+        st = lib.sv_linear_dgrad_bf16(g.data_ptr(), g.stride(0), w.data_ptr(), w.stride(0), M, N, Kin, _ACT[act],
+                                      aux.data_ptr() if aux is not None else None, aux.stride(0) if aux is not None else 0,
+                                      float(dropout_p), int(seed), dx.data_ptr(), dx.stride(0),
+                                      1 if out_dtype == torch.float32 else 0, _stream(g))
+    _lib.check(lib, st, "sv_linear_dgrad_bf16")
+    return dx
+
+
+def linear_wgrad(g, x, n_out=None, dw=None, db=None, want_db=False, accumulate=False):
+    """dw (N,Kin) f32 (+)= g[:, :N].T @ x, db (N) f32 (+)= g[:, :N].sum(0).  accumulate=True adds into the given dw / db (the
+    flat gradient buffer), otherwise they are (allocated and) overwritten."""
+    assert g.dtype == torch.bfloat16 and x.dtype == torch.bfloat16 and _rows_ok(g) and _rows_ok(x) and g.shape[0] == x.shape[0]
+    M, Kin = x.shape
+    N = g.shape[1] if n_out is None else n_out
+    if dw is None:
+        assert not accumulate
+        dw = torch.empty((N, Kin), dtype=torch.float32, device=g.device)
+    if db is None and want_db:
+        assert not accumulate
+        db = torch.empty(N, dtype=torch.float32, device=g.device)
+    assert dw.dtype == torch.float32 and dw.stride(1) == 1 and dw.shape == (N, Kin)
+    lib = _lib.gps()
+    with torch.cuda.device(g.device):
+        st = lib.sv_linear_wgrad_bf16(g.data_ptr(), g.stride(0), x.data_ptr(), x.stride(0), M, N, Kin, dw.data_ptr(),
+                                      dw.stride(0), db.data_ptr() if db is not None else None, 1 if accumulate else 0,
+                                      _stream(g))
+    _lib.check(lib, st, "sv_linear_wgrad_bf16")
+    return dw, db
+
+
+def act_bwd(g, aux, act):
+    """g * act'(aux): (M,N) bf16; relu: aux = forward output, gelu: aux = pre-activation."""
+    assert g.dtype == torch.bfloat16 and aux.dtype == torch.bfloat16 and g.shape == aux.shape and _rows_ok(g) and _rows_ok(aux)
+    out = torch.empty((g.shape[0], g.shape[1]), dtype=torch.bfloat16, device=g.device)
+    lib = _lib.gps()
+    with torch.cuda.device(g.device):
+        st = lib.sv_act_bwd_bf16(g.data_ptr(), g.stride(0), aux.data_ptr(), aux.stride(0), _ACT[act], g.shape[0], g.shape[1],
+                                 out.data_ptr(), out.stride(0), _stream(g))
+    _lib.check(lib, st, "sv_act_bwd_bf16")
+    return out
+
+
+def embedding_bwd(grad_out, ids, dw, padding_idx=-1):
+    """dw[ids] += grad_out: grad_out (..., D) bf16 | f32, ids (...) int64, dw (V, D) f32 contiguous (accumulated into)."""
+    D = grad_out.shape[-1]
+    g2 = grad_out.reshape(-1, D)
+    if g2.stride(1) != 1:
+        g2 = g2.contiguous()
+    ids = ids.reshape(-1).contiguous()
+    assert ids.dtype == torch.int64 and dw.dtype == torch.float32 and dw.is_contiguous() and dw.shape[1] == D
+    assert g2.dtype in (torch.bfloat16, torch.float32) and g2.shape[0] == ids.numel()
+    lib = _lib.gps()
+    with torch.cuda.device(g2.device):
+        st = lib.sv_embedding_bwd(g2.data_ptr(), g2.stride(0), 1 if g2.dtype == torch.bfloat16 else 0, ids.data_ptr(),
+                                  ids.numel(), D, dw.shape[0], int(padding_idx if padding_idx is not None else -1),
+                                  dw.data_ptr(), _stream(g2))
+    _lib.check(lib, st, "sv_embedding_bwd")
+    return dw

@@ -8,7 +8,7 @@ import math
 import torch
 import torch.nn.functional as F
 
-NATIVE = {"linear": False,              # plain GEMM -> cuBLAS (library GEMM); fused GEMMs (SA3, fc) use native.gemm
+NATIVE = {"linear": True,               # every nn.Linear: native tcgen05 GEMM forward / dgrad / wgrad with fused epilogues
           "attention": True,            # nn.MultiheadAttention core incl. attention dropout: native tcgen05 forward + backward
           "spatial_attention": True,    # MultiHeadAttentionSpatial core: native tcgen05 forward and backward
           "calc_pairwise_locs": True,
@@ -74,28 +74,9 @@ class _SpatialAttentionRecomputeFn(torch.autograd.Function):
         return gq.to(q.dtype), gk.to(k.dtype), gv.to(v.dtype), gs.to(sw.dtype), None, None, None, None
 
 
-import os as _os
-
-# opt-in: run the two backward GEMMs of every linear on the native tcgen05 GEMM with transposed (MN-major) operands
-# instead of cuBLAS.  The kernel path is parity-tested (tests/test_gemm_gpu.py::test_gemm_transposed_operands); the
-# whole-step timing with it has not been measured yet, so the default stays on the library GEMMs.
-_NATIVE_BWD_GEMM = _os.environ.get("SVB200_NATIVE_BWD_GEMM", "0") == "1"
-
-_MM_OUT_DTYPE = [None]  # does torch.mm accept out_dtype on this build? (decided at first use)
-
-
-def _mm_f32(a, b):
-    """a @ b with bf16 operands and an fp32 result (weight gradients accumulate into fp32 parameters)."""
-    if _MM_OUT_DTYPE[0] is None:
-        try:
-            torch.mm(a[:8, :8].contiguous(), b[:8, :8].contiguous(), out_dtype=torch.float32)
-            _MM_OUT_DTYPE[0] = True
-        except Exception:
-            _MM_OUT_DTYPE[0] = False
-    if _MM_OUT_DTYPE[0]:
-        return torch.mm(a, b, out_dtype=torch.float32)
-    return torch.mm(a, b).float()
-
+DIRECT_GRAD = [False]   # set by train.PretrainStep: parameter gradients live in one flat fp32 buffer that the wgrad
+                        # kernels may accumulate into directly (red.global.add) instead of returning a tensor that
+                        # autograd's AccumulateGrad adds with one more elementwise launch per parameter
 
 # bf16 shadows of fp32 parameters, refreshed once per step with ONE multi-tensor copy (train.PretrainStep) instead of one
 # cast kernel per weight and per bias inside every linear (autocast's behaviour: ~200 tiny launches per step)
@@ -114,6 +95,13 @@ def register_shadows(module):
     refresh_shadows()
 
 
+def register_shadow_views(pairs):
+    """pairs of (parameter, bf16 view): the shadows are slices of one flat bf16 buffer that the fused optimizer kernel
+    rewrites together with the parameters (train.FlatState) — nothing to refresh."""
+    for p, s in pairs:
+        _SHADOW[id(p)] = (s, p)
+
+
 def refresh_shadows():
     """Must run after every parameter update and before the next forward that should use the shadows."""
     if _SHADOW_LISTS[0]:
@@ -128,63 +116,179 @@ def clear_shadows():
 
 def _bf16_of(p):
     e = _SHADOW.get(id(p))
-    return e[0] if e is not None and e[1] is p else p.to(torch.bfloat16)
+    return e[0] if e is not None and e[1] is p else p.detach().to(torch.bfloat16)
+
+
+def _round8(n):
+    return (n + 7) // 8 * 8
+
+
+def _rows_bf16(t, K):
+    """(..., K) -> (M, K) bf16 with a contiguous last dim, 16-byte aligned rows (what a TMA tensor map needs)."""
+    t2 = t.reshape(-1, K)
+    if t2.dtype != torch.bfloat16:
+        t2 = t2.to(torch.bfloat16)
+    if t2.stride(1) != 1 or t2.stride(0) % 8 or t2.data_ptr() % 16:
+        t2 = t2.contiguous()
+    return t2
+
+
+def _direct(p):
+    """May the wgrad kernel accumulate straight into p.grad?"""
+    return DIRECT_GRAD[0] and p is not None and p.is_leaf and p.grad is not None and p.grad.dtype == torch.float32 and \
+        p.grad.is_contiguous()
+
+
+def _f32(b):
+    return None if b is None else b.detach().float().contiguous()
+
+
+def _wgrad(g2, x2, weight, bias, n_out, k_in):
+    """Weight / bias gradient of one linear: accumulated in place into the flat gradient buffer when allowed (returns
+    (None, None)), else returned as fresh fp32 tensors."""
+    from . import native
+    if _direct(weight) and (bias is None or _direct(bias)) and x2.shape[1] == k_in:
+        native.linear_wgrad(g2, x2, n_out=n_out, dw=weight.grad, db=bias.grad if bias is not None else None, accumulate=True)
+        return None, None
+    dw, db = native.linear_wgrad(g2, x2, n_out=n_out, want_db=bias is not None)
+    return (dw if x2.shape[1] == k_in else dw[:, :k_in].contiguous()), db
 
 
 class _LinearFn(torch.autograd.Function):
-    """Training-path linear in bf16: y = x W^T + b.  The three GEMMs are plain library GEMMs (cuBLAS, the weight is cast
-    to bf16 once per call exactly as autocast would); the bias gradient — a strided ATen reduction in the reference's
-    AddmmBackward, ~2 ms per step over ~100 layers — is the native column-sum kernel; the weight gradient is produced
-    directly in fp32."""
+    """y = act(x W^T + b) on the native tcgen05 GEMM in all three directions (csrc/gemm.cu): forward with the bias /
+    activation epilogue, dgrad with the weight read as a transposed operand, wgrad split over the tokens with the bias
+    gradient riding in the same main loop.  The returned tensor is (..., round8(N)) wide (pad columns zero) so that its
+    gradient arrives with 16-byte rows; `linear` slices it.  An input width that is not a multiple of 8 (the 6-d box
+    embedding, transformers.py loc_layers) is zero-padded on the fly."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias):
+    def forward(ctx, x, weight, bias, act):
+        from . import native
+        N, K = weight.shape
         wb = _bf16_of(weight)
-        x2 = x.reshape(-1, x.shape[-1])
-        if x2.dtype != torch.bfloat16:
-            x2 = x2.to(torch.bfloat16)
-        ctx.save_for_backward(x2, wb)
-        ctx.in_shape, ctx.in_dtype = x.shape, x.dtype
-        y = F.linear(x2, wb, _bf16_of(bias) if bias is not None else None)
-        return y.view(*x.shape[:-1], -1)
+        x2 = _rows_bf16(x, K)
+        Kp = _round8(K)
+        if Kp != K:
+            x2 = F.pad(x2, (0, Kp - K))
+            wb = F.pad(wb, (0, Kp - K))
+        Np = _round8(N)
+        assert act is None or Np == N
+        M = x2.shape[0]
+        out = torch.empty((M, Np), dtype=torch.bfloat16, device=x.device)
+        if Np != N:
+            out[:, N:].zero_()
+        need_grad = any(ctx.needs_input_grad[:3])
+        pre = None
+        if act == "gelu" and need_grad:
+            out, pre = native.linear_fwd(x2, wb, _f32(bias), act, out=out, n_out=N, want_pre=True)
+        else:
+            native.linear_fwd(x2, wb, _f32(bias), act, out=out, n_out=N)
+        ctx.save_for_backward(x2, wb, out if act == "relu" else pre)
+        ctx.params = (weight, bias)
+        ctx.meta = (x.shape, x.dtype, act, N, K)
+        return out.view(*x.shape[:-1], Np)
 
     @staticmethod
     def backward(ctx, g):
         from . import native
-        x2, wb = ctx.saved_tensors
-        g2 = g.reshape(-1, g.shape[-1])
-        if g2.dtype != torch.bfloat16:
-            g2 = g2.to(torch.bfloat16)
-        g2 = g2.contiguous()
+        x2, wb, aux = ctx.saved_tensors
+        weight, bias = ctx.params
+        in_shape, in_dtype, act, N, K = ctx.meta
+        Np = _round8(N)
+        g2 = _rows_bf16(g, Np)
+        if act is not None:
+            g2 = native.act_bwd(g2, aux, act)
         dx = dw = db = None
-        native_ok = _NATIVE_BWD_GEMM and x2.is_contiguous() and wb.is_contiguous()
         if ctx.needs_input_grad[0]:
-            # dgrad: (M,N) . (N,Kin) — the weight is the transposed (MN-major) B operand
-            dx = native.gemm_ex(g2, wb, b_transposed=True) if native_ok else torch.mm(g2, wb)
-            dx = dx.view(ctx.in_shape).to(ctx.in_dtype)
-        if ctx.needs_input_grad[1]:
-            # wgrad: g^T (N,M) . x (M,Kin) — both operands transposed in memory, fp32 result
-            dw = native.gemm_ex(g2, x2, a_transposed=True, b_transposed=True, out_dtype=torch.float32) if native_ok \
-                else _mm_f32(g2.t(), x2)
-        if ctx.needs_input_grad[2]:
-            db = native.colsum(g2)
-        return dx, dw, db
+            dx = native.linear_dgrad(g2, wb, n_red=Np)
+            if dx.shape[1] != K:
+                dx = dx[:, :K]
+            dx = dx.reshape(in_shape).to(in_dtype)
+        if ctx.needs_input_grad[1] or (bias is not None and ctx.needs_input_grad[2]):
+            dw, db = _wgrad(g2, x2, weight, bias, N, K)
+        return dx, dw, db, None
+
+
+class _FFNFn(torch.autograd.Function):
+    """y = dropout_p(act(x W1^T + b1)) W2^T + b2 — the feed-forward block of every transformer layer of the stack
+    (transformers.py:135-154,300-316; BertIntermediate + BertOutput.dense) as 2 + 4 native GEMMs: activation and dropout
+    live in the first GEMM's epilogue (the mask is a counter hash, nothing is stored), their derivative in the epilogue of
+    the second layer's dgrad."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, act, p, seed):
+        from . import native
+        H, K = w1.shape
+        N = w2.shape[0]
+        wb1, wb2 = _bf16_of(w1), _bf16_of(w2)
+        x2 = _rows_bf16(x, K)
+        need_grad = any(ctx.needs_input_grad[:5])
+        pre = None
+        if act == "gelu" and need_grad:
+            h, pre = native.linear_fwd(x2, wb1, _f32(b1), act, dropout_p=p, seed=seed, want_pre=True)
+        else:
+            h = native.linear_fwd(x2, wb1, _f32(b1), act, dropout_p=p, seed=seed)
+        y = native.linear_fwd(h, wb2, _f32(b2))
+        ctx.save_for_backward(x2, wb1, wb2, h, pre)
+        ctx.params = (w1, b1, w2, b2)
+        ctx.meta = (x.shape, x.dtype, act, p, seed)
+        return y.view(*x.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import native
+        x2, wb1, wb2, h, pre = ctx.saved_tensors
+        w1, b1, w2, b2 = ctx.params
+        in_shape, in_dtype, act, p, seed = ctx.meta
+        H, K = w1.shape
+        N = w2.shape[0]
+        g2 = _rows_bf16(g, N)
+        # dL/d(pre-activation of layer 1): dgrad of layer 2 with the activation / dropout derivative in the epilogue
+        dpre = native.linear_dgrad(g2, wb2, act=act, aux=h if act == "relu" else pre, dropout_p=p, seed=seed)
+        dw2, db2 = _wgrad(g2, h, w2, b2, N, H)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = native.linear_dgrad(dpre, wb1).reshape(in_shape).to(in_dtype)
+        dw1, db1 = _wgrad(dpre, x2, w1, b1, H, K)
+        return dx, dw1, db1, dw2, db2, None, None, None
+
+
+def _native_linear_ok(x, weight):
+    return x.is_cuda and weight.is_cuda and weight.dim() == 2 and x.numel() > 0 and weight.dtype in (torch.float32, torch.bfloat16) \
+        and (x.dtype == torch.bfloat16 or _autocast_on())
 
 
 def linear(x, weight, bias=None, activation=None):
-    if x.is_cuda and weight.dtype == torch.float32 and (x.dtype == torch.bfloat16 or _autocast_on()) and \
-            torch.is_grad_enabled() and (weight.requires_grad or x.requires_grad) and weight.shape[0] % 8 == 0 and \
-            weight.shape[1] % 8 == 0 and x.numel() > 0:
-        y = _LinearFn.apply(x, weight, bias)
-    else:
-        y = F.linear(x, weight, bias)
+    """y = act(x W^T + b).  CUDA under bf16 (tensor dtype or autocast): the native GEMM family, training and inference;
+    anything else (CPU host-logic tests, the fp32 parity path): the torch formulation."""
+    if activation not in (None, "relu", "gelu"):
+        raise ValueError(activation)
+    if _native_linear_ok(x, weight):
+        N = weight.shape[0]
+        fuse = activation if N % 8 == 0 else None
+        y = _LinearFn.apply(x, weight, bias, fuse)
+        if y.shape[-1] != N:
+            y = y[..., :N]
+        if fuse is None and activation is not None:
+            y = F.relu(y) if activation == "relu" else F.gelu(y)
+        return y
+    y = F.linear(x, weight, bias)
     if activation == "relu":
         y = F.relu(y)
     elif activation == "gelu":
         y = F.gelu(y)
-    elif activation is not None:
-        raise ValueError(activation)
     return y
+
+
+def ffn(x, w1, b1, w2, b2, activation="relu", dropout_p=0.0):
+    """linear2(dropout(act(linear1(x)))); dropout_p = 0 outside training (the caller decides)."""
+    if _native_linear_ok(x, w1) and w1.shape[0] % 8 == 0 and w1.shape[1] % 8 == 0 and w2.shape[0] % 8 == 0 and \
+            b1 is not None and b2 is not None and activation in ("relu", "gelu"):
+        return _FFNFn.apply(x, w1, b1, w2, b2, activation, float(dropout_p), _next_dropout_seed() if dropout_p > 0.0 else 0)
+    h = linear(x, w1, b1, activation=activation)
+    if dropout_p > 0.0:
+        h = F.dropout(h, dropout_p, True)
+    return linear(h, w2, b2)
 
 
 def calc_pairwise_locs(obj_centers, obj_whls, eps=1e-10, pairwise_rel_type='center', spatial_dist_norm=True,
@@ -287,6 +391,8 @@ class _CrossEntropyFn(torch.autograd.Function):
         from . import _lib
         R, W = logits2d.shape
         V = n_classes if n_classes else W
+        if labels.dtype != torch.int64:
+            raise RuntimeError(f"cross_entropy: expected int64 labels, got {labels.dtype}")
         loss_rows = torch.empty(R, dtype=torch.float32, device=logits2d.device)
         need_grad = logits2d.requires_grad
         grad = torch.empty((R, W), dtype=logits2d.dtype, device=logits2d.device) if need_grad else None
@@ -297,56 +403,26 @@ class _CrossEntropyFn(torch.autograd.Function):
                 V, int(ignore_index), loss_rows.data_ptr(), grad.data_ptr() if grad is not None else None, W,
                 torch.cuda.current_stream(logits2d.device).cuda_stream)
         _lib.check(lib, st, "sv_cross_entropy_fwd_bwd_strided")
-        count = (labels != ignore_index).sum().clamp(min=1).float()
+        # same validity predicate as the kernel: a label outside [0, V) that is not ignore_index contributes nothing
+        count = ((labels != ignore_index) & (labels >= 0) & (labels < V)).sum().float()
         ctx.save_for_backward(grad, count)
-        return loss_rows.sum() / count
+        return loss_rows.sum() / count        # every row ignored: 0 / 0 = nan, like torch
 
     @staticmethod
     def backward(ctx, gout):
         grad, count = ctx.saved_tensors
-        return grad.mul_((gout / count).to(grad.dtype)), None, None, None
-
-
-class _PaddedVocabLinearFn(torch.autograd.Function):
-    """logits_p = h @ Wp^T + bp with the class dimension zero-padded to a multiple of 64, so that every row of the logits
-    and of their gradient is 16-byte aligned: the forward runs on the native tcgen05 GEMM (bias fused), the two backward
-    GEMMs on aligned library kernels (an odd class count such as BERT's 30522 otherwise drops cuBLAS to a 4x slower
-    legacy kernel).  Reference: modules/heads/pretrain_head.py:22-32 (decoder + bias)."""
-
-    @staticmethod
-    def forward(ctx, h2, weight, bias):
-        from . import native
-        V, K = weight.shape
-        Vp = (V + 63) // 64 * 64
-        wp = torch.empty((Vp, K), dtype=torch.bfloat16, device=h2.device)
-        wp[:V].copy_(weight)
-        wp[V:].zero_()
-        bp = torch.zeros(Vp, dtype=torch.float32, device=h2.device)
-        bp[:V].copy_(bias)
-        ctx.save_for_backward(h2, wp)
-        ctx.V = V
-        return native.gemm(h2, wp, bias=bp)
-
-    @staticmethod
-    def backward(ctx, gp):
-        h2, wp = ctx.saved_tensors
-        V = ctx.V
-        gp = gp.contiguous()
-        dh = gp @ wp
-        dw = (gp.t() @ h2)[:V].float()
-        db = gp.sum(0, dtype=torch.float32)[:V]
-        return dh, dw, db
+        return grad * (gout / count).to(grad.dtype), None, None, None
 
 
 def padded_vocab_linear(h, weight, bias):
-    """(..., K) -> (..., V) logits of a wide classifier.  CUDA bf16: computed as padded logits (see _PaddedVocabLinearFn);
-    the returned tensor is the (..., :V) view and carries the padded parent as `_sv_padded`, which ops.cross_entropy uses
-    to produce the padded gradient directly.  Otherwise: ops.linear."""
-    V, K = weight.shape
-    if h.is_cuda and (h.dtype == torch.bfloat16 or _autocast_on()) and K % 8 == 0 and V % 64 != 0 and bias is not None:
-        h2 = h.reshape(-1, K).to(torch.bfloat16).contiguous()
-        lp = _PaddedVocabLinearFn.apply(h2, weight, bias).view(*h.shape[:-1], -1)
-        out = lp[..., :V]
+    """(..., K) -> (..., V) logits of a wide classifier (BERT LM head, modules/heads/pretrain_head.py:22-32: decoder + bias).
+    On the native path the GEMM writes rows padded to a multiple of 8 classes (16-byte rows, pad columns zero); the returned
+    tensor is the (..., :V) view and carries the padded parent as `_sv_padded`, which ops.cross_entropy uses to produce the
+    gradient directly in the padded layout the backward GEMMs read."""
+    V = weight.shape[0]
+    if _native_linear_ok(h, weight):
+        lp = _LinearFn.apply(h, weight, bias, None)
+        out = lp[..., :V] if lp.shape[-1] != V else lp
         out._sv_padded = lp
         return out
     return linear(h, weight, bias)

@@ -135,9 +135,14 @@ class PretrainStep:
             self.flat_grads.zero()
         else:
             self.optimizer.zero_grad(set_to_none=False)
-        with torch.autocast(self.device.type, dtype=self.dtype, enabled=self.dtype != torch.float32):
-            total, _ = self.module(dict(self.static_batch))
-        total.backward()
+        # gradients live in the flat buffer: the wgrad kernels accumulate into it directly (no AccumulateGrad adds)
+        prev, ops.DIRECT_GRAD[0] = ops.DIRECT_GRAD[0], self.flat_grads is not None
+        try:
+            with torch.autocast(self.device.type, dtype=self.dtype, enabled=self.dtype != torch.float32):
+                total, _ = self.module(dict(self.static_batch))
+            total.backward()
+        finally:
+            ops.DIRECT_GRAD[0] = prev
         return total.detach()
 
     def _raw_opt(self):

@@ -19,8 +19,9 @@ shapes = [("bert300_qkv", 19200, 768, 768), ("bert300_ffn1", 19200, 3072, 768), 
 res = {}
 for name, M, N, Kin in shapes:
     gg, W, x = rnd(M, N), rnd(N, Kin), rnd(M, Kin)
-    r = {"dgrad_native_ms": t(lambda: native.gemm_ex(gg, W, b_transposed=True)), "dgrad_cublas_ms": t(lambda: gg @ W),
-         "wgrad_native_ms": t(lambda: native.gemm_ex(gg, x, a_transposed=True, b_transposed=True, out_dtype=torch.float32)),
+    dw, db = torch.zeros(N, Kin, device="cuda"), torch.zeros(N, device="cuda")
+    r = {"dgrad_native_ms": t(lambda: native.linear_dgrad(gg, W)), "dgrad_cublas_ms": t(lambda: gg @ W),
+         "wgrad_native_ms": t(lambda: native.linear_wgrad(gg, x, dw=dw, db=db, accumulate=True)),
          "wgrad_cublas_ms": t(lambda: torch.mm(gg.t(), x, out_dtype=torch.float32))}
     res[name] = {k: round(v, 4) for k, v in r.items()}
 tot = {k: round(sum(v[k] for v in res.values()), 3) for k in next(iter(res.values()))}
