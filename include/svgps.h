@@ -53,6 +53,10 @@ int sv_gemm_bf16_ex(const void *A, int lda, int a_transposed, const void *B, int
                     const float *bias, int act, const void *residual, void *out, int ldo, int out_f32, int rowmax,
                     void *stream);
 
+/* Kernel selection of the GEMM family (tests / benchmarks): 0 = heuristic (default), 1 = single-CTA tiles (M = 128 per MMA),
+ * 2 = CTA pairs (cta_group::2, M = 256 per MMA, each CTA stages half of the B tile) wherever M > 128. */
+int sv_gemm_force_ctas(int ctas);
+
 /* ---- the three GEMMs of a linear layer y = x W^T + b with their fused epilogues (same tcgen05 kernel family) ------
  * Replace F.linear and its autograd (AddmmBackward: mm, mm, sum) for every nn.Linear of the attention stack, BERT and the
  * heads (reference: modules/layers/transformers.py:115-154,188-192,285-316; modules/language/bert.py:21-26).
@@ -119,6 +123,16 @@ int sv_attention_bwd_dropout_bf16(const void *q, long long q_bs, int q_rs, const
                                   const unsigned char *key_padding_mask, const float *spatial_w,
                                   const float *pairwise_locs, const float *lse, int B, int H, int Lq, int Lk, float scale,
                                   void *dq, void *dk, void *dv, float *d_spatial_w, float *dvec, float dropout_p,
+                                  unsigned long long seed, void *stream);
+
+/* same backward with strided gradient outputs: rows of dq / dk / dv are d_rs elements apart (scene stride L * d_rs), so the
+ * three can be the column slices [0,E) [E,2E) [2E,3E) of ONE packed (B,L,3E) buffer — the gradient of a packed QKV
+ * projection, consumed by a single dgrad / wgrad GEMM (requires Lq == Lk for a shared packed buffer) */
+int sv_attention_bwd_strided_bf16(const void *q, long long q_bs, int q_rs, const void *k, long long k_bs, int k_rs,
+                                  const void *v, long long v_bs, int v_rs, const void *o, const void *d_o,
+                                  const unsigned char *key_padding_mask, const float *spatial_w,
+                                  const float *pairwise_locs, const float *lse, int B, int H, int Lq, int Lk, float scale,
+                                  void *dq, void *dk, void *dv, int d_rs, float *d_spatial_w, float *dvec, float dropout_p,
                                   unsigned long long seed, void *stream);
 
 /* Fused dropout + residual add + LayerNorm:  y = LayerNorm(residual + dropout(x)) * gamma + beta  (reference: the post-norm

@@ -91,6 +91,10 @@ _GPS_SIGS = {
                                       ctypes.c_longlong, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_float, ctypes.c_ulonglong, c_void_p],
+    "sv_attention_bwd_strided_bf16": [c_void_p, ctypes.c_longlong, c_int, c_void_p, ctypes.c_longlong, c_int, c_void_p,
+                                      ctypes.c_longlong, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                      c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                                      c_void_p, c_float, ctypes.c_ulonglong, c_void_p],
     "sv_layer_norm_fwd": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_float, ctypes.c_ulonglong,
                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "sv_layer_norm_bwd": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_float, ctypes.c_ulonglong,
@@ -99,6 +103,7 @@ _GPS_SIGS = {
     "sv_dropout_seed_offset": [c_void_p],
     "sv_colsum": [c_void_p, ctypes.c_longlong, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
     "sv_colsum_scratch_floats": [c_int],
+    "sv_gemm_force_ctas": [c_int],
     "sv_linear_fwd_bf16": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_float, ctypes.c_ulonglong,
                            c_void_p, c_int, c_int, c_void_p, c_void_p],
     "sv_linear_dgrad_bf16": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_float,

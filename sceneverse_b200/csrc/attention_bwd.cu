@@ -24,7 +24,8 @@ struct BwdArgs {
   const float *sw, *locs, *lse;      // (B,Lq,H*6) | (B,Lq,Lk,5) | (B,H,Lq)
   int B, H, Lq, Lk;
   float scale;
-  __nv_bfloat16 *dq, *dk, *dv;       // contiguous (B,L,H*64)
+  __nv_bfloat16 *dq, *dk, *dv;       // (B,L,H*64) with row stride d_rs (elements; rows of one tensor d_rs apart, scenes L * d_rs)
+  int d_rs;
   float *dsw;                        // (B,Lq,H*6) or null
   float *dvec;                       // (B,H,Lq)   D, written by SIDE 0, read by SIDE 1
   uint32_t t16;
@@ -379,7 +380,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mR1, const __grid_constant__
         tmem_wait16(q0);
         tmem_wait16(q1);
         if (rlive) {
-          __nv_bfloat16 *o = a.dq + ((size_t)b * a.Lq + ri) * E + h * DH + wg * 32;
+          __nv_bfloat16 *o = a.dq + ((size_t)b * a.Lq + ri) * a.d_rs + h * DH + wg * 32;
 #pragma unroll
           for (int hf = 0; hf < 2; ++hf) {
             uint32_t w[4], z[4];
@@ -399,7 +400,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mR1, const __grid_constant__
         }
       } else {
         // warpgroup 0 stores dV (from the dropped P^T), warpgroup 1 stores dK (from scale * dS^T)
-        __nv_bfloat16 *o = (wg == 0 ? a.dv : a.dk) + ((size_t)b * a.Lk + ri) * E + h * DH;
+        __nv_bfloat16 *o = (wg == 0 ? a.dv : a.dk) + ((size_t)b * a.Lk + ri) * a.d_rs + h * DH;
         store_row64(trow + (wg == 0 ? COL_O2 : COL_O1), o, rlive);
       }
     }
@@ -464,6 +465,19 @@ extern "C" int sv_attention_bwd_dropout_bf16(const void *q, long long q_bs, int 
                                              int H, int Lq, int Lk, float scale, void *dq, void *dk, void *dv,
                                              float *d_spatial_w, float *dvec, float dropout_p, unsigned long long seed,
                                              void *stream) {
+  return sv_attention_bwd_strided_bf16(q, q_bs, q_rs, k, k_bs, k_rs, v, v_bs, v_rs, o, d_o, key_padding_mask, spatial_w,
+                                       pairwise_locs, lse, B, H, Lq, Lk, scale, dq, dk, dv, H * attn::DH, d_spatial_w, dvec,
+                                       dropout_p, seed, stream);
+}
+
+extern "C" int sv_attention_bwd_strided_bf16(const void *q, long long q_bs, int q_rs, const void *k, long long k_bs,
+                                             int k_rs, const void *v, long long v_bs, int v_rs, const void *o,
+                                             const void *d_o, const unsigned char *key_padding_mask,
+                                             const float *spatial_w, const float *pairwise_locs, const float *lse, int B,
+                                             int H, int Lq, int Lk, float scale, void *dq, void *dk, void *dv, int d_rs,
+                                             float *d_spatial_w, float *dvec, float dropout_p, unsigned long long seed,
+                                             void *stream) {
+  if (d_rs < H * attn::DH || (d_rs % 8)) return SV_ERR_INVALID_ARG;
   if (!(dropout_p >= 0.f) || dropout_p >= 1.f) return SV_ERR_INVALID_ARG;
   if (B < 0 || H < 1 || Lq < 1 || Lk < 1 || Lq > 384 || Lk > 384) return SV_ERR_INVALID_ARG;
   if (B == 0) return SV_OK;
@@ -481,6 +495,7 @@ extern "C" int sv_attention_bwd_dropout_bf16(const void *q, long long q_bs, int 
   a.kpm = key_padding_mask; a.sw = spatial_w; a.locs = pairwise_locs; a.lse = lse;
   a.B = B; a.H = H; a.Lq = Lq; a.Lk = Lk; a.scale = scale;
   a.dq = (__nv_bfloat16 *)dq; a.dk = (__nv_bfloat16 *)dk; a.dv = (__nv_bfloat16 *)dv;
+  a.d_rs = d_rs;
   a.dsw = d_spatial_w; a.dvec = dvec;
   a.t16 = drop_threshold(dropout_p);
   a.inv_keep = 1.0f / (1.0f - dropout_p);

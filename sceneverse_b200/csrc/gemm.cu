@@ -168,15 +168,94 @@ __device__ __forceinline__ void store_chunk_bf16(const float (&v)[32], __nv_bflo
   }
 }
 
-template <int BN, int EPI>
+// ---- CTA-pair plumbing (cta_group::2): the two CTAs of a cluster sit on the two SMs of one TPC and execute ONE MMA of
+// M = 256 rows; each CTA stages its own 128 rows of A and HALF of the B tile, so per-CTA operand traffic through
+// TMA / L2 (the ~6.3 KB/clk chip-wide limit that bounds the 128 x 256 single-CTA tile at ~1.05 PFLOP/s) drops by a third
+// to a half.  Only the leader (rank 0) issues MMAs; completion is multicast to the same barrier in both CTAs. -------------
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose completion bytes are credited to a barrier that may live in the PEER CTA (the leader's `full` barrier)
+__device__ __forceinline__ void tma_load_2d_pair(void *dst, const CUtensorMap *map, int c0, int c1, uint32_t bar_cluster_addr) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar_cluster_addr)
+      : "memory");
+}
+template <int CTAS>
+__device__ __forceinline__ void mma_bf16_g(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  if (CTAS == 1) {
+    mma_bf16(d_tmem, a_desc, b_desc, idesc, accumulate);
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+template <int CTAS>
+__device__ __forceinline__ void mma_commit_g(uint64_t *bar) {
+  if (CTAS == 1) {
+    mma_commit(bar);
+  } else {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+                 : "memory");
+  }
+}
+template <int CTAS, uint32_t NCOLS>
+__device__ __forceinline__ void tmem_alloc_g(uint32_t *smem_dst) {
+  if (CTAS == 1) {
+    tmem_alloc<NCOLS>(smem_dst);
+  } else {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "n"(NCOLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+}
+template <int CTAS, uint32_t NCOLS>
+__device__ __forceinline__ void tmem_dealloc_g(uint32_t taddr) {
+  if (CTAS == 1) tmem_dealloc<NCOLS>(taddr);
+  else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+
+template <int BN, int CTAS>
+struct GemmCfg {
+  static constexpr int BNL = BN / CTAS;                         // B rows staged by one CTA
+  static constexpr int A_STAGE = BM * BK * 2, B_STAGE = BNL * BK * 2;
+  static constexpr int STAGES_RAW = (192 * 1024) / (A_STAGE + B_STAGE);
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr size_t SMEM = (size_t)STAGES * (A_STAGE + B_STAGE) + 2048 + (2 * STAGES + 4) * 8 + 16 + 8 * STG_BYTES + 2 * BN * 4;
+};
+
+template <int BN, int EPI, int CTAS>
 __global__ void __launch_bounds__(320, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GemmArgs g) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  constexpr int A_STAGE = BM * BK * 2, B_STAGE = BN * BK * 2;
-  constexpr uint32_t ACC_COLS = 2 * BN;                       // bias-gradient accumulators (WGRAD) live behind these
-  constexpr uint32_t TMEM_COLS = (EPI == EPI_WGRAD ? ACC_COLS + 64 : ACC_COLS) <= 128 ? 128
-                                 : (EPI == EPI_WGRAD ? ACC_COLS + 64 : ACC_COLS) <= 256 ? 256 : 512;
-  static_assert((EPI == EPI_WGRAD ? ACC_COLS + 64 : ACC_COLS) <= 512, "TMEM budget");
+  using Cfg = GemmCfg<BN, CTAS>;
+  constexpr int BNL = Cfg::BNL, A_STAGE = Cfg::A_STAGE, B_STAGE = Cfg::B_STAGE, STAGES = Cfg::STAGES;
+  // a weight gradient keeps the bias-gradient sums in 32 spare columns per accumulator; at BN = 256 that leaves room for
+  // one accumulator only (the K loop of a weight gradient is long, the un-overlapped epilogue is a few percent)
+  constexpr int ACC_BUFS = (EPI == EPI_WGRAD && BN == 256) ? 1 : 2;
+  constexpr uint32_t ACC_COLS = ACC_BUFS * BN;
+  constexpr uint32_t NEED_COLS = EPI == EPI_WGRAD ? ACC_COLS + 32 * ACC_BUFS : ACC_COLS;
+  constexpr uint32_t TMEM_COLS = NEED_COLS <= 128 ? 128 : NEED_COLS <= 256 ? 256 : 512;
+  static_assert(NEED_COLS <= 512, "TMEM budget");
+  static_assert(BNL % 8 == 0, "B half-tile rows");
   uint8_t *sA = smem;
   uint8_t *sB = smem + STAGES * A_STAGE;
   uint8_t *sOnes = sB + STAGES * B_STAGE;                      // [16][64] bf16 ones (2 KB), WGRAD bias-gradient operand
@@ -189,7 +268,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
   float *sbias = stage + 8 * STG_BYTES / 4;                     // [2][BN] bias slice of the tile, double-buffered
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tiles_m = (g.M + BM - 1) / BM, tiles_n = (g.N + BN - 1) / BN;
+  const uint32_t rank = CTAS == 2 ? cluster_rank() : 0u;
+  const int unit = blockIdx.x / CTAS, n_units = gridDim.x / CTAS;       // a unit = one CTA, or one CTA pair
+  const int tiles_m = (g.M + CTAS * BM - 1) / (CTAS * BM), tiles_n = (g.N + BN - 1) / BN;
   const int n_tiles = tiles_m * tiles_n;
   const int k_steps = (g.K + BK - 1) / BK;
   const int kps = (k_steps + g.splits - 1) / g.splits;   // K steps per split (host guarantees every split is non-empty)
@@ -203,7 +284,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(acc_full + b, 1);
-      mbar_init(acc_empty + b, 256);
+      mbar_init(acc_empty + b, CTAS * 8);    // one arrival per epilogue warp of every CTA of the unit
     }
     mbar_fence_init();
   }
@@ -211,54 +292,73 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     for (int i = threadIdx.x; i < 512; i += 320) reinterpret_cast<uint32_t *>(sOnes)[i] = 0x3F803F80u;  // bf16 1.0 pairs
     fence_proxy_async_smem();
   }
-  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+  if (warp == 1) tmem_alloc_g<CTAS, TMEM_COLS>(tmem_slot);
   fence_before_sync();
   __syncthreads();
+  if (CTAS == 2) cluster_sync_all();     // the peer's barriers are initialised before anything remote touches them
   fence_after_sync();
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
-    // ------------------------------- TMA producer -------------------------------
+    // ------------------------------- TMA producer (every CTA stages its own rows of A and its share of B) -------------
     if (lane == 0) {
       uint32_t it = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      for (int item = unit; item < n_items; item += n_units) {
         const int t = item % n_tiles, sp = item / n_tiles;
-        const int m0 = (t % tiles_m) * BM, n0 = (t / tiles_m) * BN;
+        const int m0 = ((t % tiles_m) * CTAS + (int)rank) * BM, n0 = (t / tiles_m) * BN + (int)rank * BNL;
         const int ks0 = sp * kps, ks1 = min(k_steps, ks0 + kps);
         for (int ks = ks0; ks < ks1; ++ks, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1u;
           mbar_wait(empty + s, ph ^ 1u);  // slot free (first pass returns immediately)
-          mbar_expect_tx(full + s, A_STAGE + B_STAGE);
           const int k0 = ks * BK;
-          if (g.a_mn) {  // [K][M] storage: one [BK x 64] box per 64 rows of the tile
+          if (CTAS == 1) {
+            mbar_expect_tx(full + s, A_STAGE + B_STAGE);
+            if (g.a_mn) {  // [K][M] storage: one [BK x 64] box per 64 rows of the tile
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j) tma_load_2d(sA + s * A_STAGE + j * (BK * 128), &mapA, m0 + j * 64, k0, full + s);
-          } else {
-            tma_load_2d(sA + s * A_STAGE, &mapA, k0, m0, full + s);
-          }
-          if (g.b_mn) {
+              for (int j = 0; j < BM / 64; ++j) tma_load_2d(sA + s * A_STAGE + j * (BK * 128), &mapA, m0 + j * 64, k0, full + s);
+            } else {
+              tma_load_2d(sA + s * A_STAGE, &mapA, k0, m0, full + s);
+            }
+            if (g.b_mn) {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sB + s * B_STAGE + j * (BK * 128), &mapB, n0 + j * 64, k0, full + s);
+              for (int j = 0; j < BNL / 64; ++j) tma_load_2d(sB + s * B_STAGE + j * (BK * 128), &mapB, n0 + j * 64, k0, full + s);
+            } else {
+              tma_load_2d(sB + s * B_STAGE, &mapB, k0, n0, full + s);
+            }
           } else {
-            tma_load_2d(sB + s * B_STAGE, &mapB, k0, n0, full + s);
+            // both CTAs' bytes are credited to the LEADER's barrier (only the leader's MMA thread waits on it)
+            if (rank == 0) mbar_expect_tx(full + s, 2 * (A_STAGE + B_STAGE));
+            const uint32_t fb = map_to_rank(smem_u32(full + s), 0);
+            if (g.a_mn) {
+#pragma unroll
+              for (int j = 0; j < BM / 64; ++j) tma_load_2d_pair(sA + s * A_STAGE + j * (BK * 128), &mapA, m0 + j * 64, k0, fb);
+            } else {
+              tma_load_2d_pair(sA + s * A_STAGE, &mapA, k0, m0, fb);
+            }
+            if (g.b_mn) {
+#pragma unroll
+              for (int j = 0; j < BNL / 64; ++j) tma_load_2d_pair(sB + s * B_STAGE + j * (BK * 128), &mapB, n0 + j * 64, k0, fb);
+            } else {
+              tma_load_2d_pair(sB + s * B_STAGE, &mapB, k0, n0, fb);
+            }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------- MMA issuer -------------------------------
-    if (lane == 0) {
-      const uint32_t IDESC = make_idesc_bf16(BM, BN) | (g.a_mn ? 1u << 15 : 0u) | (g.b_mn ? 1u << 16 : 0u);
-      const uint32_t IDESC_ONES = make_idesc_bf16(BM, 16) | (g.a_mn ? 1u << 15 : 0u);   // B = K-major tile of ones
+    // ------------------------------- MMA issuer (leader CTA only) -------------------------------
+    if (lane == 0 && rank == 0) {
+      const uint32_t IDESC = make_idesc_bf16(CTAS * BM, BN) | (g.a_mn ? 1u << 15 : 0u) | (g.b_mn ? 1u << 16 : 0u);
+      const uint32_t IDESC_ONES = make_idesc_bf16(CTAS * BM, 16) | (g.a_mn ? 1u << 15 : 0u);   // B = K-major tile of ones
       const uint64_t ones_desc = make_desc_sw128(smem_u32(sOnes));
       uint32_t it = 0, tl = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++tl) {
+      for (int item = unit; item < n_items; item += n_units, ++tl) {
         const int t = item % n_tiles, sp = item / n_tiles;
         const bool bias_tile = with_bias_grad && (t / tiles_m) == 0;
         const int ks0 = sp * kps, ks1 = min(k_steps, ks0 + kps);
-        const int b = tl & 1;
-        mbar_wait(acc_empty + b, ((tl >> 1) & 1u) ^ 1u);  // epilogue drained this accumulator
+        const int b = tl % ACC_BUFS;
+        mbar_wait(acc_empty + b, ((tl / ACC_BUFS) & 1u) ^ 1u);  // every epilogue warp of the unit drained this accumulator
         fence_after_sync();
         for (int ks = ks0; ks < ks1; ++ks, ++it) {
           const int s = it % STAGES;
@@ -268,14 +368,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
 #pragma unroll
           for (int kk = 0; kk < BK / 16; ++kk) {
             const uint64_t adesc = g.a_mn ? make_desc_sw128_mn(a0 + kk * 2048) : make_desc_sw128(a0 + kk * 32);
-            mma_bf16(tmem + b * BN, adesc, g.b_mn ? make_desc_sw128_mn(b0 + kk * 2048) : make_desc_sw128(b0 + kk * 32), IDESC,
-                     (ks != ks0) || kk != 0);
+            mma_bf16_g<CTAS>(tmem + b * BN, adesc, g.b_mn ? make_desc_sw128_mn(b0 + kk * 2048) : make_desc_sw128(b0 + kk * 32),
+                             IDESC, (ks != ks0) || kk != 0);
             if (EPI == EPI_WGRAD && bias_tile)
-              mma_bf16(tmem + ACC_COLS + b * 32, adesc, ones_desc, IDESC_ONES, (ks != ks0) || kk != 0);
+              mma_bf16_g<CTAS>(tmem + ACC_COLS + b * 32, adesc, ones_desc, IDESC_ONES, (ks != ks0) || kk != 0);
           }
-          mma_commit(empty + s);  // frees the smem slot when these MMAs retire
+          mma_commit_g<CTAS>(empty + s);  // frees the smem slot (in both CTAs) when these MMAs retire
         }
-        mma_commit(acc_full + b);
+        mma_commit_g<CTAS>(acc_full + b);
       }
     }
   } else {
@@ -290,20 +390,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     uint8_t *stg = reinterpret_cast<uint8_t *>(stage) + (warp - 2) * STG_BYTES;
     const unsigned long long seed = (EPI != EPI_WGRAD && g.t16) ? attn::effective_seed(g.seed, g.seed_offset) : 0ull;
     uint32_t tl = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++tl) {
+    for (int item = unit; item < n_items; item += n_units, ++tl) {
       const int t = item % n_tiles;
-      const int b = tl & 1;
-      const int m0 = (t % tiles_m) * BM, n0 = (t / tiles_m) * BN;
+      const int b = tl % ACC_BUFS;
+      const int m0 = ((t % tiles_m) * CTAS + (int)rank) * BM, n0 = (t / tiles_m) * BN;
       const int row = m0 + row_in_tile;
       const int wrow0 = m0 + q * 32;  // first accumulator row of this warp
-      float *sb = sbias + b * BN;
+      float *sb = sbias + (tl & 1) * BN;
       if (EPI == EPI_FWD) {
         if (et < BN) sb[et] = (g.bias != nullptr && n0 + et < g.N) ? __ldg(g.bias + n0 + et) : 0.f;
         asm volatile("bar.sync 1, 256;" ::: "memory");  // bias visible; everybody is done with the tile before last
       }
       uint32_t rk = 0;
       if (EPI != EPI_WGRAD && g.t16) rk = attn::drop_row_key(seed, (unsigned long long)row);
-      mbar_wait(acc_full + b, (tl >> 1) & 1u);
+      mbar_wait(acc_full + b, (tl / ACC_BUFS) & 1u);
       fence_after_sync();
       const uint32_t taddr = tmem + b * BN + half * (BN / 2) + ((uint32_t)(q * 32) << 16);
       uint32_t rr[2][32];
@@ -427,13 +527,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         attn::tmem_wait16(r16);
         if (row < g.M) atomicAdd(g.bias_grad + row, __uint_as_float(r16[0]));
       }
+      // this warp has finished reading the accumulator: one arrival per warp on the LEADER's barrier
       fence_before_sync();
-      mbar_arrive(acc_empty + b);
+      __syncwarp();
+      if (lane == 0) {
+        if (CTAS == 1) mbar_arrive(acc_empty + b);
+        else mbar_arrive_cluster(map_to_rank(smem_u32(acc_empty + b), 0));
+      }
     }
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem);
+  if (CTAS == 2) cluster_sync_all();     // no CTA of the pair exits (or frees TMEM) while the other may still signal it
+  if (warp == 1) tmem_dealloc_g<CTAS, TMEM_COLS>(tmem);
 }
 
 using attn::EncodeTiledFn;
@@ -481,10 +587,10 @@ int device_sms(int *dev_out) {
   return sms_of_dev[dev];
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int CTAS>
 int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mb, const GemmArgs &g, cudaStream_t st) {
-  constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 2048 + (2 * STAGES + 4) * 8 + 16 + 8 * STG_BYTES + 2 * BN * 4;
-  auto kern = gemm_kernel<BN, EPI>;
+  constexpr size_t smem = GemmCfg<BN, CTAS>::SMEM;
+  auto kern = gemm_kernel<BN, EPI, CTAS>;
   static bool configured[64] = {false};
   int dev = 0;
   const int sms = device_sms(&dev);
@@ -494,25 +600,49 @@ int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mb, const GemmArgs &g,
     if (rc) return rc;
     configured[dev] = true;
   }
-  const int items = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN) * g.splits;
-  const int grid = items < sms ? items : sms;
-  kern<<<grid, 320, smem, st>>>(ma, mb, g);
+  const int units = ((g.M + CTAS * BM - 1) / (CTAS * BM)) * ((g.N + BN - 1) / BN) * g.splits;
+  const int max_units = sms / CTAS;
+  const int grid = (units < max_units ? units : max_units) * CTAS;
+  if (CTAS == 1) {
+    kern<<<grid, 320, smem, st>>>(ma, mb, g);
+  } else {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(320);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ma, mb, g);
+    if (e != cudaSuccess) {
+      sv::t_last_cuda_error = (int)e;
+      cudaGetLastError();
+      return SV_ERR_CUDA;
+    }
+  }
   return sv::after_launch();
 }
 
-// Tile width: the persistent grid runs ceil(tiles / SMs) waves, so the cheapest width is the one whose LAST wave is
-// fullest; relative cost of one tile by width (MMA time + the fixed per-tile overhead; narrow tiles are shared-memory
-// operand-bandwidth bound) measured on the B200.
-int pick_bn(int M, int N, int sms, bool allow256) {
+// Tile width: the persistent grid runs ceil(tiles / units) waves, so the cheapest width is the one whose LAST wave is
+// fullest; relative cost of one tile by width (MMA time + the fixed per-tile overhead; narrow tiles are operand-bandwidth
+// bound).  `mn_b`: B is a transposed (MN-major) operand staged in 64-column slabs, so a CTA pair needs BN / 2 % 64 == 0.
+int pick_bn(int M, int N, int units, int ctas, bool allow256, bool mn_b) {
   const int cand[4] = {256, 192, 128, 64};
   const float w[4] = {1.00f, 0.78f, 0.56f, 0.34f};
-  int best = 64;
+  int best = 0;
   float best_cost = 1e30f;
-  const int tm = (M + BM - 1) / BM;
+  const int tm = (M + ctas * BM - 1) / (ctas * BM);
   for (int i = 0; i < 4; ++i) {
     if (cand[i] == 256 && !allow256) continue;
+    if (ctas == 2 && mn_b && (cand[i] / 2) % 64) continue;
+    if (ctas == 2 && cand[i] == 64) continue;
     const int tiles = tm * ((N + cand[i] - 1) / cand[i]);
-    const float cost = (float)((tiles + sms - 1) / sms) * w[i];
+    const float cost = (float)((tiles + units - 1) / units) * w[i];
     if (cost < best_cost - 1e-6f) {
       best_cost = cost;
       best = cand[i];
@@ -521,41 +651,47 @@ int pick_bn(int M, int N, int sms, bool allow256) {
   return best;
 }
 
-template <int EPI>
+template <int EPI, int CTAS>
 int dispatch(int bn, const CUtensorMap &ma, const CUtensorMap &mb, const GemmArgs &g, cudaStream_t st) {
-  if (bn == 256) {
-    if constexpr (EPI == EPI_WGRAD) return SV_ERR_INVALID_ARG;   // 2 x 256 accumulator columns leave no room for the bias sums
-    else return launch_gemm<256, EPI>(ma, mb, g, st);
-  }
-  if (bn == 192) return launch_gemm<192, EPI>(ma, mb, g, st);
-  if (bn == 128) return launch_gemm<128, EPI>(ma, mb, g, st);
-  return launch_gemm<64, EPI>(ma, mb, g, st);
+  if (bn == 256) return launch_gemm<256, EPI, CTAS>(ma, mb, g, st);
+  if (bn == 192) return launch_gemm<192, EPI, CTAS>(ma, mb, g, st);
+  if (bn == 128) return launch_gemm<128, EPI, CTAS>(ma, mb, g, st);
+  if constexpr (CTAS == 1) return launch_gemm<64, EPI, 1>(ma, mb, g, st);
+  return SV_ERR_INVALID_ARG;
 }
+
+int g_force_ctas = 0;   // tests / benchmarks: 1 or 2 forces the single-CTA or the CTA-pair kernel, 0 = heuristic
 
 int run_gemm(int epi, const void *A, int lda, int a_t, const void *B, int ldb, int b_t, GemmArgs &g, cudaStream_t st) {
   const int M = g.M, N = g.N, K = g.K;
   if (M < 0 || N < 0 || K < 0) return SV_ERR_INVALID_ARG;
   if (M == 0 || N == 0) return SV_OK;
   if (!A || !B || !g.out || K < 1 || (lda % 8) || (ldb % 8)) return SV_ERR_INVALID_ARG;
-  if (a_t ? lda < M : (lda < K || (K % 8))) return SV_ERR_INVALID_ARG;
-  if (b_t ? ldb < N : (ldb < K || (K % 8))) return SV_ERR_INVALID_ARG;
+  if (a_t ? lda < M : lda < K) return SV_ERR_INVALID_ARG;   // K itself may be anything: TMA zero-fills past the extent
+  if (b_t ? ldb < N : ldb < K) return SV_ERR_INVALID_ARG;
   if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) return SV_ERR_INVALID_ARG;
   int dev = 0;
   const int sms = device_sms(&dev);
   if (sms == 0) return SV_ERR_INVALID_ARG;
   g.a_mn = a_t ? 1 : 0;
   g.b_mn = b_t ? 1 : 0;
-  const int bn = pick_bn(M, N, sms, epi != EPI_WGRAD);
+  // CTA pairs (M = 256 per MMA) whenever there are at least two 128-row tiles and enough work to fill the pairs
+  int ctas = (M > BM && (long long)M * N >= 256ll * 128 * (sms / 2)) ? 2 : 1;
+  if (g_force_ctas == 1 || g_force_ctas == 2) ctas = (g_force_ctas == 2 && M > BM) ? 2 : 1;
+  if (g.rowmax) ctas = 1;
+  const int units = sms / ctas;
+  const int bn = pick_bn(M, N, units, ctas, true, b_t != 0);
+  if (bn == 0) return SV_ERR_INVALID_ARG;
   g.splits = 1;
   if (epi == EPI_WGRAD && g.red_out) {
     // split-K: the output of a weight gradient is small (a few dozen tiles), the contraction runs over every token
-    const int tiles = ((M + BM - 1) / BM) * ((N + bn - 1) / bn), k_steps = (K + BK - 1) / BK;
+    const int tiles = ((M + ctas * BM - 1) / (ctas * BM)) * ((N + bn - 1) / bn), k_steps = (K + BK - 1) / BK;
     float best_eff = 0.f;
-    for (int s = 1; s <= 16 && s * 4 <= k_steps; ++s) {
+    for (int s = 1; s <= 32 && s * 4 <= k_steps; ++s) {
       const int kps = (k_steps + s - 1) / s;
       if ((s - 1) * kps >= k_steps) continue;  // an empty split
       const int items = tiles * s;
-      const float eff = (float)items / (float)(((items + sms - 1) / sms) * sms) - 0.01f * s;
+      const float eff = (float)items / (float)(((items + units - 1) / units) * units) - 0.005f * s;
       if (eff > best_eff) {
         best_eff = eff;
         g.splits = s;
@@ -565,11 +701,16 @@ int run_gemm(int epi, const void *A, int lda, int a_t, const void *B, int ldb, i
   CUtensorMap ma, mb;
   int rc = a_t ? make_map_mn(&ma, A, M, K, lda) : make_map(&ma, A, M, K, lda, BM);
   if (rc) return rc;
-  rc = b_t ? make_map_mn(&mb, B, N, K, ldb) : make_map(&mb, B, N, K, ldb, bn);
+  rc = b_t ? make_map_mn(&mb, B, N, K, ldb) : make_map(&mb, B, N, K, ldb, bn / ctas);
   if (rc) return rc;
-  if (epi == EPI_FWD) return dispatch<EPI_FWD>(bn, ma, mb, g, st);
-  if (epi == EPI_DGRAD) return dispatch<EPI_DGRAD>(bn, ma, mb, g, st);
-  return dispatch<EPI_WGRAD>(bn, ma, mb, g, st);
+  if (ctas == 2) {
+    if (epi == EPI_FWD) return dispatch<EPI_FWD, 2>(bn, ma, mb, g, st);
+    if (epi == EPI_DGRAD) return dispatch<EPI_DGRAD, 2>(bn, ma, mb, g, st);
+    return dispatch<EPI_WGRAD, 2>(bn, ma, mb, g, st);
+  }
+  if (epi == EPI_FWD) return dispatch<EPI_FWD, 1>(bn, ma, mb, g, st);
+  if (epi == EPI_DGRAD) return dispatch<EPI_DGRAD, 1>(bn, ma, mb, g, st);
+  return dispatch<EPI_WGRAD, 1>(bn, ma, mb, g, st);
 }
 
 void set_dropout(GemmArgs &g, float p, unsigned long long seed) {
@@ -580,6 +721,11 @@ void set_dropout(GemmArgs &g, float p, unsigned long long seed) {
 }
 
 }  // namespace
+
+extern "C" int sv_gemm_force_ctas(int ctas) {
+  g_force_ctas = ctas;
+  return SV_OK;
+}
 
 extern "C" int sv_gemm_bf16(const void *A, int lda, const void *B, int ldb, int M, int N, int K, const float *bias,
                             int act, const void *residual, void *out, int ldo, int out_f32, int rowmax, void *stream) {

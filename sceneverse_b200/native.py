@@ -58,16 +58,24 @@ def attention(q, k, v, num_heads, key_padding_mask=None, spatial_w=None, spatial
 
 
 def attention_backward(q, k, v, out, grad_out, lse, num_heads, key_padding_mask=None, spatial_w=None, pairwise_locs=None,
-                       dropout_p=0.0, seed=0):
-    """Gradients of `attention` (gate requires one weight set per head).  Returns (dq, dk, dv, d_spatial_w or None)."""
+                       dropout_p=0.0, seed=0, packed_grad=None):
+    """Gradients of `attention` (gate requires one weight set per head).  Returns (dq, dk, dv, d_spatial_w or None).
+    packed_grad: a (B, L, 3E) bf16 buffer (self-attention on a packed QKV projection): dq / dk / dv are written straight
+    into its three column slices and returned as views."""
     B, Lq, E = q.shape
     Lk = k.shape[1]
     dev = q.device
     grad_out = grad_out.to(torch.bfloat16).contiguous()
     out = out.contiguous()
-    dq = torch.empty((B, Lq, E), dtype=torch.bfloat16, device=dev)
-    dk = torch.empty((B, Lk, E), dtype=torch.bfloat16, device=dev)
-    dv = torch.empty((B, Lk, E), dtype=torch.bfloat16, device=dev)
+    if packed_grad is not None:
+        assert Lq == Lk and packed_grad.shape == (B, Lq, 3 * E) and packed_grad.is_contiguous() and packed_grad.dtype == torch.bfloat16
+        dq, dk, dv = packed_grad[..., :E], packed_grad[..., E:2 * E], packed_grad[..., 2 * E:]
+        d_rs = 3 * E
+    else:
+        dq = torch.empty((B, Lq, E), dtype=torch.bfloat16, device=dev)
+        dk = torch.empty((B, Lk, E), dtype=torch.bfloat16, device=dev)
+        dv = torch.empty((B, Lk, E), dtype=torch.bfloat16, device=dev)
+        d_rs = E
     dvec = torch.empty((B, num_heads, Lq), dtype=torch.float32, device=dev)
     kpm = key_padding_mask.to(torch.uint8).contiguous() if key_padding_mask is not None else None
     sw = locs = dsw = None
@@ -76,14 +84,14 @@ def attention_backward(q, k, v, out, grad_out, lse, num_heads, key_padding_mask=
         dsw = torch.empty_like(sw)
     lib = _lib.gps()
     with torch.cuda.device(dev):
-        st = lib.sv_attention_bwd_dropout_bf16(
+        st = lib.sv_attention_bwd_strided_bf16(
             q.data_ptr(), q.stride(0), q.stride(1), k.data_ptr(), k.stride(0), k.stride(1), v.data_ptr(), v.stride(0),
             v.stride(1), out.data_ptr(), grad_out.data_ptr(), kpm.data_ptr() if kpm is not None else None,
             sw.data_ptr() if sw is not None else None, locs.data_ptr() if locs is not None else None, lse.data_ptr(),
-            B, num_heads, Lq, Lk, 0.125, dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
+            B, num_heads, Lq, Lk, 0.125, dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), d_rs,
             dsw.data_ptr() if dsw is not None else None, dvec.data_ptr(), float(dropout_p), int(seed),
             torch.cuda.current_stream(dev).cuda_stream)
-    _lib.check(lib, st, "sv_attention_bwd_dropout_bf16")
+    _lib.check(lib, st, "sv_attention_bwd_strided_bf16")
     return dq, dk, dv, dsw
 
 
@@ -221,3 +229,8 @@ def embedding_bwd(grad_out, ids, dw, padding_idx=-1):
                                   dw.data_ptr(), _stream(g2))
     _lib.check(lib, st, "sv_embedding_bwd")
     return dw
+
+
+def gemm_force_ctas(n):
+    """0 = heuristic, 1 = single-CTA tiles, 2 = CTA pairs (cta_group::2) wherever the problem has more than 128 rows."""
+    _lib.check(_lib.gps(), _lib.gps().sv_gemm_force_ctas(int(n)), "sv_gemm_force_ctas")

@@ -52,6 +52,58 @@ class _AttentionFn(torch.autograd.Function):
         return dq, dk, dv, dsw, None, None, None, None, None, None
 
 
+class _AttentionPackedFn(torch.autograd.Function):
+    """Self-attention on a PACKED projection qkv (B,L,3E) = [q | k | v]: the kernels read the three column slices through
+    strided TMA maps and the backward writes dq | dk | dv into ONE packed gradient, so the projection's backward is a
+    single dgrad + a single wgrad GEMM (no split / cat / add kernels in between)."""
+
+    @staticmethod
+    def forward(ctx, qkv, sw, locs, kpm, n_head, spatial_n_head, dropout_p, seed):
+        from . import native
+        E = qkv.shape[-1] // 3
+        q, k, v = qkv[..., :E], qkv[..., E:2 * E], qkv[..., 2 * E:]
+        out, lse = native.attention(q, k, v, n_head, key_padding_mask=kpm, spatial_w=sw, spatial_heads=spatial_n_head,
+                                    pairwise_locs=locs, return_lse=True, dropout_p=dropout_p, seed=seed)
+        ctx.save_for_backward(qkv, out, lse, sw, locs, kpm)
+        ctx.n_head, ctx.drop = n_head, (dropout_p, seed)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        from . import native
+        qkv, out, lse, sw, locs, kpm = ctx.saved_tensors
+        E = qkv.shape[-1] // 3
+        q, k, v = qkv[..., :E], qkv[..., E:2 * E], qkv[..., 2 * E:]
+        dqkv = torch.empty(qkv.shape, dtype=torch.bfloat16, device=qkv.device)
+        _, _, _, dsw = native.attention_backward(q, k, v, out, grad_out, lse, ctx.n_head, key_padding_mask=kpm, spatial_w=sw,
+                                                 pairwise_locs=locs, dropout_p=ctx.drop[0], seed=ctx.drop[1], packed_grad=dqkv)
+        return dqkv, dsw, None, None, None, None, None, None
+
+
+def _packed_ok(qkv, num_heads):
+    E = qkv.shape[-1] // 3
+    return qkv.is_cuda and qkv.dtype == torch.bfloat16 and qkv.dim() == 3 and qkv.shape[-1] == 3 * E and E == num_heads * 64 \
+        and qkv.is_contiguous() and qkv.shape[1] <= 384
+
+
+def attention_packed(qkv, num_heads, key_padding_mask=None, dropout_p=0.0):
+    """Self-attention on qkv (B,L,3E) = [q | k | v] -> (B,L,E)."""
+    if _packed_ok(qkv, num_heads):
+        return _AttentionPackedFn.apply(qkv, None, None, key_padding_mask, num_heads, 0, float(dropout_p),
+                                        _next_dropout_seed() if dropout_p > 0.0 else 0)
+    q, k, v = qkv.chunk(3, dim=-1)
+    return attention(q, k, v, num_heads, key_padding_mask=key_padding_mask, dropout_p=dropout_p)
+
+
+def spatial_attention_packed(qkv, spatial_weights, pairwise_locs, n_head, spatial_n_head, key_padding_mask=None):
+    """MultiHeadAttentionSpatial core on a packed projection; returns (out, None)."""
+    if _packed_ok(qkv, n_head) and spatial_n_head == n_head:
+        return _AttentionPackedFn.apply(qkv, spatial_weights.float(), pairwise_locs.float(), key_padding_mask, n_head,
+                                        spatial_n_head, 0.0, 0), None
+    q, k, v = qkv.chunk(3, dim=-1)
+    return spatial_attention(q, k, v, spatial_weights, pairwise_locs, n_head, spatial_n_head, key_padding_mask=key_padding_mask)
+
+
 class _SpatialAttentionRecomputeFn(torch.autograd.Function):
     """Native forward, torch-recompute backward: only for a gate shared across heads (spatial_multihead=False)."""
 
@@ -200,7 +252,7 @@ class _LinearFn(torch.autograd.Function):
             g2 = native.act_bwd(g2, aux, act)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = native.linear_dgrad(g2, wb, n_red=Np)
+            dx = native.linear_dgrad(g2, wb, n_red=N)      # the true class count: the weight has no pad rows to read
             if dx.shape[1] != K:
                 dx = dx[:, :K]
             dx = dx.reshape(in_shape).to(in_dtype)

@@ -130,11 +130,12 @@ class PretrainStep:
     # ---- CUDA-graph path ---------------------------------------------------------------------------------------------
     def _raw_fwd_bwd(self):
         self._step_counter.add_(1)
-        ops.refresh_shadows()      # one multi-tensor fp32 -> bf16 copy of all weights (instead of a cast per linear)
         if self.flat_grads is not None:
             self.flat_grads.zero()
         else:
             self.optimizer.zero_grad(set_to_none=False)
+        if self.flat_grads is None or not isinstance(self.flat_grads, FlatState):
+            ops.refresh_shadows()
         # gradients live in the flat buffer: the wgrad kernels accumulate into it directly (no AccumulateGrad adds)
         prev, ops.DIRECT_GRAD[0] = ops.DIRECT_GRAD[0], self.flat_grads is not None
         try:
@@ -146,6 +147,9 @@ class PretrainStep:
         return total.detach()
 
     def _raw_opt(self):
+        if isinstance(self.flat_grads, FlatState):
+            self.flat_grads.optimizer_step()                    # native: clip + AdamW + bf16 shadows, one pass
+            return
         if self.grad_norm is not None:
             if self.flat_grads is not None:
                 self.flat_grads.clip_norm_(self.grad_norm)     # same math as clip_grad_norm_, two kernels on the flat buffer
@@ -163,17 +167,24 @@ class PretrainStep:
     def _advance_lr(self):
         self._sched_step += 1
         f = self._lr_lambda(self._sched_step)
+        if isinstance(self.flat_grads, FlatState):
+            self.flat_grads.lr_factor.fill_(f)
+            return
         for g, base in zip(self.optimizer.param_groups, self._base_lrs):
             g['lr'].fill_(base * f)
 
     def _capture(self, data_dict):
         self.static_batch = {k: v.clone() for k, v in data_dict.items() if torch.is_tensor(v)}
-        if self.dtype == torch.bfloat16:
-            ops.clear_shadows()
-            ops.register_shadows(self.module)
         if self.dp_graph:
             sync_module_state(self.module)
-        self.flat_grads = FlatGrads(self.parameters())
+        ops.clear_shadows()
+        kw = dict(self.cfg.solver.optim.args)
+        self.flat_grads = FlatState(self.optimizer.param_groups, self._base_lrs, betas=tuple(kw.get("betas", (0.9, 0.999))),
+                                    eps=float(kw.get("eps", 1e-8)), max_norm=self.grad_norm)
+        self.flat_grads.lr_factor.fill_(self._lr_lambda(self._sched_step))
+        register_packs(self.module, self.flat_grads)
+        if self.dtype == torch.bfloat16:
+            ops.register_shadows(self.module)       # whatever bf16 linears read outside the flat buffer (frozen parameters)
         cur = torch.cuda.current_stream(self.device)
         side = torch.cuda.Stream(self.device)
         side.wait_stream(cur)
@@ -277,6 +288,108 @@ class FlatGrads:
             else:
                 dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
                 self.flat.div_(dist.get_world_size(group))
+
+
+class FlatState(FlatGrads):
+    """Parameters, gradients, AdamW moments and the bf16 weight shadows of the trainable parameters as slices of FIVE flat
+    buffers with one layout (parameter-group by parameter-group, every tensor starting on a 16-byte boundary of the bf16
+    copy).  What that buys:
+      * clip_grad_norm_ + AdamW + the fp32 -> bf16 shadow refresh are ONE pass over HBM (csrc/train_ops.cu adamw_flat_kernel:
+        read p, g, m, v; write p, m, v, bf16 p) after a squared-norm pass over g — instead of torch's multi-tensor AdamW
+        (16 launches), 2 clipping launches and a 65-launch shadow copy;
+      * the data-parallel mean is one NCCL call on `flat` (as before);
+      * sibling projections that read the same input (w_qs | w_ks | w_vs of the spatial attention, query | key | value of
+        BERT) are ADJACENT in every buffer, so [3E, E] views of the shadow / gradient buffers let ops.linear_packed run them
+        as one GEMM in each direction."""
+    ALIGN = 8
+
+    def __init__(self, groups, base_lrs, betas=(0.9, 0.999), eps=1e-8, max_norm=None):
+        params, segs, off = [], [], 0
+        for g, lr in zip(groups, base_lrs):
+            ps = [p for p in g['params'] if p.requires_grad]
+            if not ps:
+                continue
+            begin = off
+            for p in ps:
+                params.append((p, off))
+                off += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+            segs.append((begin, off, float(lr), float(g.get('weight_decay', 0.0))))
+        dev = params[0][0].device
+        self.params = [p for p, _ in params]
+        self.n = off
+        self.flat_p = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.flat = torch.zeros(off, dtype=torch.float32, device=dev)          # gradients (name kept from FlatGrads)
+        self.exp_avg = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.shadow = torch.zeros(off, dtype=torch.bfloat16, device=dev)
+        self.offsets = {}
+        pairs = []
+        for p, o in params:
+            n = p.numel()
+            self.flat_p[o:o + n].copy_(p.detach().reshape(-1))
+            p.data = self.flat_p[o:o + n].view_as(p)
+            p.grad = self.flat[o:o + n].view_as(p)
+            pairs.append((p, self.shadow[o:o + n].view_as(p)))
+            self.offsets[id(p)] = o
+        self.shadow.copy_(self.flat_p)
+        ops.register_shadow_views(pairs)
+        import numpy as np
+        seg_dt = np.dtype([("begin", "<i8"), ("end", "<i8"), ("lr_scale", "<f4"), ("weight_decay", "<f4")])
+        self.segments = torch.from_numpy(np.array(segs, dtype=seg_dt).view(np.uint8).copy()).to(dev)
+        self.nseg = len(segs)
+        self.betas, self.eps, self.max_norm = betas, eps, max_norm
+        self.lr_factor = torch.ones(1, dtype=torch.float32, device=dev)
+        self.step_t = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.grad_norm_t = torch.zeros(1, dtype=torch.float32, device=dev)
+        from . import _lib
+        self.scratch = torch.zeros(_lib.gps().sv_adamw_scratch_floats(), dtype=torch.float32, device=dev)
+
+    def packed_views(self, params):
+        """[sum N, K] / [sum N] views of the shadow, gradient and parameter buffers spanning `params` if they are adjacent
+        in the flat layout (same trailing shape, no alignment gaps), else None."""
+        offs = [self.offsets.get(id(p)) for p in params]
+        if any(o is None for o in offs):
+            return None
+        tail = params[0].shape[1:]
+        o = offs[0]
+        for p, po in zip(params, offs):
+            if po != o or p.shape[1:] != tail:
+                return None
+            o += p.numel()
+        rows = sum(p.shape[0] for p in params)
+        sl = slice(offs[0], o)
+        return (self.shadow[sl].view(rows, *tail), self.flat[sl].view(rows, *tail), self.flat_p[sl].view(rows, *tail))
+
+    def optimizer_step(self):
+        """clip (max_norm) + AdamW + shadow refresh; the step counter lives on the device (CUDA-graph replay safe)."""
+        from . import _lib
+        lib = _lib.gps()
+        self.step_t.add_(1)
+        with torch.cuda.device(self.flat.device):
+            st = lib.sv_adamw_flat(self.flat_p.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
+                                   self.flat.data_ptr(), self.shadow.data_ptr(), self.n, self.segments.data_ptr(), self.nseg,
+                                   float(self.max_norm) if self.max_norm is not None else 0.0, self.lr_factor.data_ptr(),
+                                   self.step_t.data_ptr(), 1.0, float(self.betas[0]), float(self.betas[1]), float(self.eps),
+                                   self.scratch.data_ptr(), self.grad_norm_t.data_ptr(),
+                                   torch.cuda.current_stream(self.flat.device).cuda_stream)
+        _lib.check(lib, st, "sv_adamw_flat")
+
+
+def register_packs(module, flat):
+    """Tell ops.linear_packed which sibling projections are adjacent in the flat buffers."""
+    from .modules.layers import MultiHeadAttentionSpatial
+    for m in module.modules():
+        trip = None
+        if isinstance(m, MultiHeadAttentionSpatial):
+            trip = (m.w_qs, m.w_ks, m.w_vs)
+        elif all(hasattr(m, a) and isinstance(getattr(m, a), nn.Linear) for a in ("query", "key", "value")):
+            trip = (m.query, m.key, m.value)       # HF BertSelfAttention
+        if trip is None or any(l.bias is None for l in trip):
+            continue
+        w = flat.packed_views([l.weight for l in trip])
+        b = flat.packed_views([l.bias for l in trip])
+        if w is not None and b is not None:
+            ops.register_pack([l.weight for l in trip], [l.bias for l in trip], w, b)
 
 
 def sync_module_state(module, src=0):

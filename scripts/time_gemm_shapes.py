@@ -3,6 +3,7 @@ import os, sys, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from sceneverse_b200 import native
+native.gemm_force_ctas(int(os.environ.get("SVB200_GEMM_CTAS", "0")))
 quick = len(sys.argv) > 1 and sys.argv[1] == "quick"
 def t(fn, n=10):
     if quick:

@@ -4,6 +4,7 @@ import os, sys, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from sceneverse_b200 import native
+native.gemm_force_ctas(int(os.environ.get("SVB200_GEMM_CTAS", "0")))
 g = torch.Generator(device="cuda").manual_seed(0)
 def rnd(*s): return (torch.randn(*s, device="cuda", generator=g) * 0.5).bfloat16()
 def t(fn, n=10):

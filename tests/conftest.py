@@ -31,3 +31,18 @@ def ref_ext():
         return build_ref_ext.load_prebuilt()
     except Exception:  # pragma: no cover
         return None
+
+
+@pytest.fixture(autouse=True)
+def _reset_process_wide_native_state():
+    """A test that dies between registering and clearing a process-wide hook (device dropout-seed counter, bf16 weight
+    shadows, direct gradient accumulation) must not change what the following tests compute."""
+    yield
+    import sys
+    ops = sys.modules.get("sceneverse_b200.ops")
+    if ops is not None:
+        ops.DIRECT_GRAD[0] = False
+        ops.clear_shadows()
+    lib = sys.modules.get("sceneverse_b200._lib")
+    if lib is not None and "libsvgps.so" in lib._cache:
+        lib.gps().sv_dropout_seed_offset(None)

@@ -16,6 +16,15 @@ def rnd(*s, seed=0, scale=0.5):
     return torch.randn(*s, device="cuda", generator=g) * scale
 
 
+@pytest.fixture(params=[0, 1, 2], ids=["auto", "cta1", "cta2"])
+def ctas(request):
+    """Every shape runs on the single-CTA kernels, on the CTA-pair (cta_group::2) kernels and under the heuristic."""
+    from sceneverse_b200 import native
+    native.gemm_force_ctas(request.param)
+    yield request.param
+    native.gemm_force_ctas(0)
+
+
 def rel(got, want):
     return (got.float() - want.float()).abs().max().item() / (want.float().abs().max().item() + 1e-9)
 
@@ -23,7 +32,7 @@ def rel(got, want):
 @pytest.mark.parametrize("M,N,K", [(8320, 2304, 768), (19200, 768, 3072), (5120, 72, 768), (130, 768, 768), (3, 768, 768),
                                    (1000, 600, 136), (3200, 3072, 768)])
 @pytest.mark.parametrize("act", [None, "relu", "gelu"])
-def test_linear_fwd_epilogues(M, N, K, act):
+def test_linear_fwd_epilogues(M, N, K, act, ctas):
     from sceneverse_b200 import native
     x, w, b = rnd(M, K).bfloat16(), rnd(N, K, scale=K ** -0.5).bfloat16(), rnd(N, seed=1)
     out, pre = native.linear_fwd(x, w, b, act, want_pre=True)
@@ -35,7 +44,7 @@ def test_linear_fwd_epilogues(M, N, K, act):
 
 
 @pytest.mark.parametrize("act", ["relu", "gelu"])
-def test_linear_fwd_dropout_mask_is_the_documented_hash(act):
+def test_linear_fwd_dropout_mask_is_the_documented_hash(act, ctas):
     from sceneverse_b200 import native
     M, N, K, p, seed = 777, 2048, 768, 0.1, 123456789
     x, w, b = rnd(M, K).bfloat16(), rnd(N, K, scale=K ** -0.5).bfloat16(), rnd(N, seed=1)
@@ -49,7 +58,7 @@ def test_linear_fwd_dropout_mask_is_the_documented_hash(act):
 
 
 @pytest.mark.parametrize("M,N,Kin", [(8320, 768, 2048), (19200, 3072, 768), (5120, 2304, 768), (100, 8, 384), (3200, 30528, 768)])
-def test_linear_dgrad_plain(M, N, Kin):
+def test_linear_dgrad_plain(M, N, Kin, ctas):
     from sceneverse_b200 import native
     g, w = rnd(M, N).bfloat16(), rnd(N, Kin, scale=N ** -0.5).bfloat16()
     got = native.linear_dgrad(g, w, out_dtype=torch.float32)
@@ -57,7 +66,7 @@ def test_linear_dgrad_plain(M, N, Kin):
 
 
 @pytest.mark.parametrize("act,p", [("relu", 0.0), ("relu", 0.1), ("gelu", 0.0), ("gelu", 0.1)])
-def test_linear_dgrad_activation_derivative_epilogue(act, p):
+def test_linear_dgrad_activation_derivative_epilogue(act, p, ctas):
     """dgrad of layer 2 of an FFN with d/dpre of dropout(act(pre)) fused: against autograd of the same expression."""
     from sceneverse_b200 import native
     M, N, H, seed = 1000, 768, 2048, 424242
@@ -74,7 +83,7 @@ def test_linear_dgrad_activation_derivative_epilogue(act, p):
 
 @pytest.mark.parametrize("M,N,Kin", [(19200, 768, 768), (8320, 2304, 768), (19200, 3072, 768), (8320, 768, 2048), (5120, 72, 768),
                                      (2, 768, 768), (333, 607, 384), (3200, 30522, 768)])
-def test_linear_wgrad_split_k_bias_and_accumulate(M, N, Kin):
+def test_linear_wgrad_split_k_bias_and_accumulate(M, N, Kin, ctas):
     from sceneverse_b200 import native
     Np = (N + 7) // 8 * 8
     g = torch.zeros(M, Np, device="cuda", dtype=torch.bfloat16)

