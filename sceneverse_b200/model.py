@@ -53,15 +53,13 @@ def _bert_self_attention_forward(self, hidden_states, attention_mask=None, past_
     """BertSelfAttention through ops.attention (native tcgen05 forward / backward with in-kernel attention dropout on
     CUDA bf16).  `attention_mask` is the padding mask HF prepared for its SDPA path: None, or (B,1,Lq,Lk) with True /
     0.0 = attend (identical rows), from which the (B,Lk) key-padding mask is read back."""
-    q = ops.linear(hidden_states, self.query.weight, self.query.bias)
-    k = ops.linear(hidden_states, self.key.weight, self.key.bias)
-    v = ops.linear(hidden_states, self.value.weight, self.value.bias)
+    qkv = ops.linear_packed(hidden_states, [self.query, self.key, self.value])   # one GEMM, [q | k | v]
     kpm = None
     if attention_mask is not None:
         row = attention_mask[:, 0, 0, :]
         kpm = row.logical_not() if row.dtype == torch.bool else row < 0
-    out = ops.attention(q, k, v, self.num_attention_heads, key_padding_mask=kpm,
-                        dropout_p=self.dropout.p if self.training else 0.0)
+    out = ops.attention_packed(qkv, self.num_attention_heads, key_padding_mask=kpm,
+                               dropout_p=self.dropout.p if self.training else 0.0)
     return out, None
 
 

@@ -95,7 +95,10 @@ class MultiheadAttention(nn.Module):
         E, H = self.embed_dim, self.num_heads
         w, b = self.in_proj_weight, self.in_proj_bias
         if key is query and value is query:
-            q, k, v = ops.linear(query, w, b).split(E, dim=-1)
+            # packed projection -> attention on the packed tensor: one dgrad + one wgrad GEMM in the backward
+            out = ops.attention_packed(ops.linear(query, w, b), H, key_padding_mask=key_padding_mask,
+                                       dropout_p=self.dropout if self.training else 0.0)
+            return ops.linear(out, self.out_proj.weight, self.out_proj.bias), None
         else:
             q = ops.linear(query, w[:E], b[:E])
             k, v = ops.linear(key, w[E:], b[E:]).split(E, dim=-1) if key is value else \
@@ -125,10 +128,15 @@ class MultiHeadAttentionSpatial(nn.Module):
 
     def forward(self, q, k, v, pairwise_locs, key_padding_mask=None, txt_embeds=None):
         residual = q
+        sw = ops.linear(residual, self.lang_cond_fc.weight, self.lang_cond_fc.bias)  # (b,l,h*(d+1)): [bias,w1..wd] per head
+        if k is q and v is q:    # self-attention (every GPS call site): the three projections are one GEMM
+            qkv = ops.linear_packed(q, [self.w_qs, self.w_ks, self.w_vs])
+            out, attn = ops.spatial_attention_packed(qkv, sw, pairwise_locs, self.n_head, self.spatial_n_head,
+                                                     key_padding_mask=key_padding_mask)
+            return ops.linear(out, self.fc.weight, self.fc.bias), attn
         qh = ops.linear(q, self.w_qs.weight, self.w_qs.bias)
         kh = ops.linear(k, self.w_ks.weight, self.w_ks.bias)
         vh = ops.linear(v, self.w_vs.weight, self.w_vs.bias)
-        sw = ops.linear(residual, self.lang_cond_fc.weight, self.lang_cond_fc.bias)  # (b,l,h*(d+1)): [bias,w1..wd] per head
         out, attn = ops.spatial_attention(qh, kh, vh, sw, pairwise_locs, self.n_head, self.spatial_n_head,
                                           key_padding_mask=key_padding_mask)
         return ops.linear(out, self.fc.weight, self.fc.bias), attn

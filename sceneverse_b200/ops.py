@@ -164,6 +164,16 @@ def clear_shadows():
     _SHADOW.clear()
     _SHADOW_LISTS[0].clear()
     _SHADOW_LISTS[1].clear()
+    _PACKS.clear()
+
+
+# sibling projections (q | k | v) whose weights / biases are adjacent in the flat buffers of train.FlatState:
+# ids of the weights -> ([3E,K] bf16 shadow view, [3E,K] gradient view, [3E] fp32 bias view, [3E] bias-gradient view)
+_PACKS = {}
+
+
+def register_pack(weights, biases, wviews, bviews):
+    _PACKS[tuple(id(w) for w in weights)] = (wviews[0], wviews[1], bviews[2], bviews[1], list(weights) + list(biases))
 
 
 def _bf16_of(p):
@@ -303,6 +313,56 @@ class _FFNFn(torch.autograd.Function):
             dx = native.linear_dgrad(dpre, wb1).reshape(in_shape).to(in_dtype)
         dw1, db1 = _wgrad(dpre, x2, w1, b1, H, K)
         return dx, dw1, db1, dw2, db2, None, None, None
+
+
+class _PackedLinearFn(torch.autograd.Function):
+    """[y1 | y2 | ...] = x [W1; W2; ...]^T + [b1 | b2 | ...]: sibling projections of one input (w_qs / w_ks / w_vs of
+    MultiHeadAttentionSpatial, transformers.py:190-192; query / key / value of BertSelfAttention) as ONE GEMM per direction.
+    With train.FlatState the stacked weight, bias and their gradients are views of the flat buffers (no copies, the wgrad
+    accumulates in place); otherwise the stack is concatenated per call."""
+
+    @staticmethod
+    def forward(ctx, x, *params):
+        from . import native
+        n = len(params) // 2
+        ws, bs = params[:n], params[n:]
+        pack = _PACKS.get(tuple(id(w) for w in ws))
+        if pack is not None:
+            wb, bias = pack[0], pack[2]
+        else:
+            wb = torch.cat([_bf16_of(w) for w in ws], 0)
+            bias = torch.cat([b.detach().float() for b in bs], 0)
+        K = wb.shape[1]
+        x2 = _rows_bf16(x, K)
+        out = native.linear_fwd(x2, wb, bias)
+        ctx.save_for_backward(x2, wb)
+        ctx.params, ctx.pack, ctx.meta = params, pack, (x.shape, x.dtype)
+        return out.view(*x.shape[:-1], wb.shape[0])
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import native
+        x2, wb = ctx.saved_tensors
+        params, pack = ctx.params, ctx.pack
+        n = len(params) // 2
+        in_shape, in_dtype = ctx.meta
+        g2 = _rows_bf16(g, wb.shape[0])
+        dx = native.linear_dgrad(g2, wb).reshape(in_shape).to(in_dtype) if ctx.needs_input_grad[0] else None
+        if pack is not None and all(_direct(p) for p in params):
+            native.linear_wgrad(g2, x2, dw=pack[1], db=pack[3], accumulate=True)
+            return (dx,) + (None,) * len(params)
+        dw, db = native.linear_wgrad(g2, x2, want_db=True)
+        rows = [w.shape[0] for w in params[:n]]
+        return (dx,) + tuple(dw.split(rows, 0)) + tuple(db.split(rows, 0))
+
+
+def linear_packed(x, linears):
+    """cat([lin(x) for lin in linears], -1) for nn.Linear modules with bias that share the input width."""
+    ws = [l.weight for l in linears]
+    if _native_linear_ok(x, ws[0]) and all(l.bias is not None and l.weight.shape[0] % 8 == 0 for l in linears) and \
+            ws[0].shape[1] % 8 == 0:
+        return _PackedLinearFn.apply(x, *ws, *[l.bias for l in linears])
+    return torch.cat([linear(x, l.weight, l.bias) for l in linears], dim=-1)
 
 
 def _native_linear_ok(x, weight):

@@ -249,3 +249,59 @@ def test_backward_matches_reference_gradients_cpu_fp32():
         got = dict(mods[mname].named_parameters())[n].grad.reshape(-1)[:96].numpy()
         assert np.abs(got - G[key]).max() <= 1e-4 * (np.abs(G[key]).max() + 1e-8), key
 
+
+
+@pytest.mark.gpu
+def test_graph_step_matches_eager_step_parameters():
+    """One optimisation step through the captured path (flat parameter / gradient / moment buffers, wgrad kernels accumulating
+    into the flat gradient, native clip + AdamW) must move every parameter like the eager step (torch autograd accumulation,
+    clip_grad_norm_, torch.optim.AdamW) from the same initial state, batch and dropout-free modules."""
+    from sceneverse_b200 import model as M, train
+    tf = weights.synthetic_tensor("text_features", (607, 768))
+    d = synthetic.scene_batch(9, B=4, O=80, P=1024, L=50, Ls=300)
+    batch = {k: torch.from_numpy(v).cuda() for k, v in d.items()}
+
+    def make(graph):
+        cfg = M.pretrain_config(1, text_features=tf)
+        cfg["solver"]["sched"]["args"]["warmup_steps"] = 1
+        ps = train.PretrainStep(cfg, "cuda", dtype=torch.bfloat16, seed=3, cuda_graph=graph)
+        for m in ps.module.modules():          # no dropout: both paths must be deterministic functions of the batch
+            if isinstance(m, torch.nn.Dropout):
+                m.p = 0.0
+            if hasattr(m, "dropout") and isinstance(m.dropout, float):
+                m.dropout = 0.0
+        return ps
+    eager, graph = make(False), make(True)
+    graph.module.load_state_dict(eager.module.state_dict())
+    p0 = {n: p.detach().clone() for n, p in eager.module.named_parameters()}
+    eager._probe_unused(dict(batch))
+    graph._probe_unused(dict(batch))
+    # eager reference: one step
+    eager.step(dict(batch))
+    # graph path: the same single step, run eagerly on the flat state (what the capture records)
+    graph.static_batch = {k: v.clone() for k, v in batch.items()}
+    from sceneverse_b200 import ops
+    kw = dict(graph.cfg.solver.optim.args)
+    graph.flat_grads = train.FlatState(graph.optimizer.param_groups, graph._base_lrs, betas=tuple(kw.get("betas", (0.9, 0.999))),
+                                       eps=float(kw.get("eps", 1e-8)), max_norm=graph.grad_norm)
+    graph.flat_grads.lr_factor.fill_(eager._lr_lambda(0) if False else 1.0)
+    lr_scale = float(eager.optimizer.param_groups[0]["lr"]) / eager.optimizer.param_groups[0]["initial_lr"] \
+        if "initial_lr" in eager.optimizer.param_groups[0] else None
+    train.register_packs(graph.module, graph.flat_grads)
+    graph._raw_step()
+    ops.clear_shadows()
+    worst = (0.0, None)
+    for (n, pe), (_, pg) in zip(eager.module.named_parameters(), graph.module.named_parameters()):
+        if not pe.requires_grad:
+            continue
+        de, dg = (pe.detach() - p0[n]).float(), (pg.detach() - p0[n]).float()
+        # AdamW's first step moves every coordinate by ~lr * sign(g): compare update DIRECTIONS and sizes where the gradient
+        # is not noise-level
+        scale = de.abs().max().item() + 1e-12
+        big = de.abs() > 0.5 * scale
+        if big.sum() == 0:
+            continue
+        agree = (torch.sign(de[big]) == torch.sign(dg[big])).float().mean().item()
+        worst = min(worst, (agree - 1.0, n)) if worst[1] else (agree - 1.0, n)
+        assert agree > 0.97, (n, agree)
+    print("GRAPH_VS_EAGER worst sign agreement", 1.0 + worst[0], worst[1])

@@ -175,3 +175,27 @@ def test_embedding_backward_scatter_add():
     emb = torch.nn.Embedding(1000, 768, padding_idx=0).cuda()
     emb(ids).backward(g.float())
     assert rel(dw, emb.weight.grad) < 1e-5
+
+
+def test_linear_packed_and_attention_packed_match_the_unpacked_path():
+    """q | k | v as ONE projection GEMM + attention on the packed tensor (strided TMA maps, dq | dk | dv written into one packed
+    gradient) must equal three separate linears + ops.attention, forward and backward."""
+    from sceneverse_b200 import ops
+    B, L, E, H = 8, 130, 768, 12
+    x = rnd(B, L, E).bfloat16().requires_grad_(True)
+    lins = [torch.nn.Linear(E, E).cuda() for _ in range(3)]
+    kpm = torch.zeros(B, L, dtype=torch.bool, device="cuda")
+    kpm[:, 100:] = True
+    go = rnd(B, L, E, seed=7).bfloat16()
+    out = ops.attention_packed(ops.linear_packed(x, lins), H, key_padding_mask=kpm)
+    out.backward(go)
+    got = [out.detach(), x.grad.clone()] + [p.grad.clone() for l in lins for p in (l.weight, l.bias)]
+    x.grad = None
+    for l in lins:
+        l.weight.grad = l.bias.grad = None
+    q, k, v = (ops.linear(x, l.weight, l.bias) for l in lins)
+    ref = ops.attention(q, k, v, H, key_padding_mask=kpm)
+    ref.backward(go)
+    want = [ref.detach(), x.grad] + [p.grad for l in lins for p in (l.weight, l.bias)]
+    for g, w, name in zip(got, want, ["out", "dx", "dWq", "dbq", "dWk", "dbk", "dWv", "dbv"]):
+        assert rel(g, w) < 1e-2, name
