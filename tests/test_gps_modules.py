@@ -263,7 +263,7 @@ def test_graph_step_matches_eager_step_parameters():
 
     def make(graph):
         cfg = M.pretrain_config(1, text_features=tf)
-        cfg["solver"]["sched"]["args"]["warmup_steps"] = 1
+        cfg["solver"]["sched"]["args"]["warmup_steps"] = 0      # lr factor 1 from the first step
         ps = train.PretrainStep(cfg, "cuda", dtype=torch.bfloat16, seed=3, cuda_graph=graph)
         for m in ps.module.modules():          # no dropout: both paths must be deterministic functions of the batch
             if isinstance(m, torch.nn.Dropout):
@@ -284,24 +284,25 @@ def test_graph_step_matches_eager_step_parameters():
     kw = dict(graph.cfg.solver.optim.args)
     graph.flat_grads = train.FlatState(graph.optimizer.param_groups, graph._base_lrs, betas=tuple(kw.get("betas", (0.9, 0.999))),
                                        eps=float(kw.get("eps", 1e-8)), max_norm=graph.grad_norm)
-    graph.flat_grads.lr_factor.fill_(eager._lr_lambda(0) if False else 1.0)
-    lr_scale = float(eager.optimizer.param_groups[0]["lr"]) / eager.optimizer.param_groups[0]["initial_lr"] \
-        if "initial_lr" in eager.optimizer.param_groups[0] else None
+    graph.flat_grads.lr_factor.fill_(graph._lr_lambda(0))
     train.register_packs(graph.module, graph.flat_grads)
     graph._raw_step()
     ops.clear_shadows()
-    worst = (0.0, None)
+    worst = (1.0, None)
+    checked = 0
     for (n, pe), (_, pg) in zip(eager.module.named_parameters(), graph.module.named_parameters()):
-        if not pe.requires_grad:
+        if not pe.requires_grad or pe.grad is None:
+            continue
+        ge = pe.grad.float()
+        big = ge.abs() > 0.2 * ge.abs().max()          # coordinates whose gradient is far above the bf16 noise
+        if big.sum() == 0 or ge.abs().max() == 0:
             continue
         de, dg = (pe.detach() - p0[n]).float(), (pg.detach() - p0[n]).float()
-        # AdamW's first step moves every coordinate by ~lr * sign(g): compare update DIRECTIONS and sizes where the gradient
-        # is not noise-level
-        scale = de.abs().max().item() + 1e-12
-        big = de.abs() > 0.5 * scale
-        if big.sum() == 0:
-            continue
+        # the first AdamW step moves a coordinate by -lr * g / (|g| + eps): same sign and (almost) the same size in both paths
         agree = (torch.sign(de[big]) == torch.sign(dg[big])).float().mean().item()
-        worst = min(worst, (agree - 1.0, n)) if worst[1] else (agree - 1.0, n)
-        assert agree > 0.97, (n, agree)
-    print("GRAPH_VS_EAGER worst sign agreement", 1.0 + worst[0], worst[1])
+        ratio = (dg[big].abs().mean() / (de[big].abs().mean() + 1e-20)).item()
+        worst = min(worst, (agree, n))
+        checked += 1
+        assert agree > 0.98 and 0.9 < ratio < 1.1, (n, agree, ratio)
+    assert checked > 100, checked
+    print("GRAPH_VS_EAGER worst sign agreement", worst, "parameters checked", checked)
