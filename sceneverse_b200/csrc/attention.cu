@@ -129,17 +129,33 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
     // ---- pass 1: row maximum of the scaled, masked logits (the gate is <= 0, so this bounds the gated logits too) ----
     float m2 = -INFINITY;
     if (wlive) {
+      // TMEM loads are software-pipelined: unit u + 1 is in flight while unit u is reduced (tcgen05.wait::ld retires every
+      // load issued before it, so the next load is issued right after the wait)
+      uint32_t ra[16], rb[16];
+      if (u_begin < u_end) tmem_ld16_async(trow + u_begin * 16, ra);
 #pragma unroll 1
-      for (int u = u_begin; u < u_end; ++u) {
-        uint32_t r[16];
-        tmem_ld16_async(trow + u * 16, r);
-        tmem_wait16(r);
-        const float4 *kb4 = reinterpret_cast<const float4 *>(kb + u * 16);
+      for (int u = u_begin; u < u_end; u += 2) {
+        tmem_wait16(ra);
+        if (u + 1 < u_end) tmem_ld16_async(trow + (u + 1) * 16, rb);
+        {
+          const float4 *kb4 = reinterpret_cast<const float4 *>(kb + u * 16);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const float4 k4 = kb4[g];
-          m2 = fmaxf(m2, fmaxf(fmaxf(fmaf(u2f(r[4 * g]), c2, k4.x), fmaf(u2f(r[4 * g + 1]), c2, k4.y)),
-                               fmaxf(fmaf(u2f(r[4 * g + 2]), c2, k4.z), fmaf(u2f(r[4 * g + 3]), c2, k4.w))));
+          for (int g = 0; g < 4; ++g) {
+            const float4 k4 = kb4[g];
+            m2 = fmaxf(m2, fmaxf(fmaxf(fmaf(u2f(ra[4 * g]), c2, k4.x), fmaf(u2f(ra[4 * g + 1]), c2, k4.y)),
+                                 fmaxf(fmaf(u2f(ra[4 * g + 2]), c2, k4.z), fmaf(u2f(ra[4 * g + 3]), c2, k4.w))));
+          }
+        }
+        if (u + 1 < u_end) {
+          tmem_wait16(rb);
+          if (u + 2 < u_end) tmem_ld16_async(trow + (u + 2) * 16, ra);
+          const float4 *kb4 = reinterpret_cast<const float4 *>(kb + (u + 1) * 16);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const float4 k4 = kb4[g];
+            m2 = fmaxf(m2, fmaxf(fmaxf(fmaf(u2f(rb[4 * g]), c2, k4.x), fmaf(u2f(rb[4 * g + 1]), c2, k4.y)),
+                                 fmaxf(fmaf(u2f(rb[4 * g + 2]), c2, k4.z), fmaf(u2f(rb[4 * g + 3]), c2, k4.w))));
+          }
         }
       }
     }
@@ -151,11 +167,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
     // ---- pass 2: p = 2^(x - max), row sum, dropout, bf16 P tile ------------------------------------------------------------
     float sum = 0.f;
     if (wlive) {
+      uint32_t rn[16];                      // next unit's S columns (in flight behind the current unit's math)
+      if (u_begin < u_end) tmem_ld16_async(trow + u_begin * 16, rn);
 #pragma unroll 1
       for (int u = u_begin; u < u_end; ++u) {
         const int j0 = u * 16;
         uint32_t r[16];
-        tmem_ld16_async(trow + j0, r);
         float g2[16];
         if (GATED) {
 #pragma unroll
@@ -184,7 +201,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
             }
           }
         }
-        tmem_wait16(r);
+        tmem_wait16(rn);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r[i] = rn[i];
+        if (u + 1 < u_end) tmem_ld16_async(trow + j0 + 16, rn);
         const float4 *kb4 = reinterpret_cast<const float4 *>(kb + j0);
         float p[16];
 #pragma unroll

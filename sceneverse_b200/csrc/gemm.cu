@@ -5,8 +5,11 @@
 //
 //   C[M,N] = epilogue( A[M,K] x B[N,K]^T ),  bf16 operands, fp32 accumulation in TMEM
 //
-// Roles (320 threads): warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator + MMA issuer (one lane),
-// warps 2..9 = epilogue (two warps per TMEM lane quadrant, each thread one accumulator row x half of the columns).
+// Roles (448 threads): warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator + MMA issuer (one lane),
+// warps 2..13 = epilogue (three warps per TMEM lane quadrant, each thread one accumulator row, the 32-column chunks of the
+// tile dealt round-robin to the three).  With K = 768 (most linears of the stack) a tile's main loop is only 12 K steps,
+// so the epilogue — TMEM load, bias / activation math, staged coalesced stores — is what bounds the kernel: ncu showed the
+// 8-warp version at 94 % busy epilogue warps and 57 % tensor pipe (profiles/r2_gemm_ncu_summary.json).
 // Operand tiles travel global -> shared by TMA (cp.async.bulk.tensor.2d, 128-byte rows, SWIZZLE_128B) through a 4-stage
 // mbarrier ring; either operand may be stored transposed in memory ([K][rows]) and is then staged as 64-column slabs and
 // read MN-major by the tensor core — the dgrad / wgrad forms of a linear layer need no transposed copy.  Accumulators
@@ -34,6 +37,7 @@ namespace {
 using namespace tc05;
 
 constexpr int BM = 128, BK = 64, STAGES = 4;
+constexpr int EPI_WARPS = 12, EPI_PARTS = 3, NTHREADS = 64 + 32 * EPI_WARPS;
 constexpr int STG_BYTES = 32 * 80;  // per epilogue warp: 32 rows x (64 B + 16 B pad); also holds the [32][17] f32 row-max scratch
 constexpr int EPI_FWD = 0, EPI_DGRAD = 1, EPI_WGRAD = 2;
 
@@ -54,6 +58,8 @@ struct GemmArgs {
   float inv_keep;
   unsigned long long seed;
   const unsigned long long *seed_offset;
+  int n_fast;               // tile order of the work list: 1 = column tiles vary fastest (A panels stream once, B stays in
+                            // L2), 0 = row tiles vary fastest (the reverse); chosen by operand size
   int splits;               // split-K factor (>= 1); > 1 only with red_out
   int red_out;              // WGRAD: accumulate into out with red.global.add instead of storing
   float *bias_grad;         // WGRAD: [M] += row sums of A (the bias gradient), or null
@@ -239,11 +245,11 @@ struct GemmCfg {
   static constexpr int A_STAGE = BM * BK * 2, B_STAGE = BNL * BK * 2;
   static constexpr int STAGES_RAW = (192 * 1024) / (A_STAGE + B_STAGE);
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr size_t SMEM = (size_t)STAGES * (A_STAGE + B_STAGE) + 2048 + (2 * STAGES + 4) * 8 + 16 + 8 * STG_BYTES + 2 * BN * 4;
+  static constexpr size_t SMEM = (size_t)STAGES * (A_STAGE + B_STAGE) + 2048 + (2 * STAGES + 4) * 8 + 16 + EPI_WARPS * STG_BYTES + 2 * BN * 4;
 };
 
 template <int BN, int EPI, int CTAS>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(NTHREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GemmArgs g) {
   extern __shared__ __align__(1024) uint8_t smem[];
   using Cfg = GemmCfg<BN, CTAS>;
@@ -264,8 +270,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
   uint64_t *acc_full = empty + STAGES;   // [2]
   uint64_t *acc_empty = acc_full + 2;    // [2]
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
-  float *stage = reinterpret_cast<float *>(tmem_slot + 4);  // [8 warps][STG_BYTES] store staging / row-max transpose scratch
-  float *sbias = stage + 8 * STG_BYTES / 4;                     // [2][BN] bias slice of the tile, double-buffered
+  float *stage = reinterpret_cast<float *>(tmem_slot + 4);  // [EPI_WARPS][STG_BYTES] store staging / row-max transpose scratch
+  float *sbias = stage + EPI_WARPS * STG_BYTES / 4;             // [2][BN] bias slice of the tile, double-buffered
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = CTAS == 2 ? cluster_rank() : 0u;
@@ -284,12 +290,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(acc_full + b, 1);
-      mbar_init(acc_empty + b, CTAS * 8);    // one arrival per epilogue warp of every CTA of the unit
+      mbar_init(acc_empty + b, CTAS * EPI_WARPS);    // one arrival per epilogue warp of every CTA of the unit
     }
     mbar_fence_init();
   }
   if (EPI == EPI_WGRAD) {
-    for (int i = threadIdx.x; i < 512; i += 320) reinterpret_cast<uint32_t *>(sOnes)[i] = 0x3F803F80u;  // bf16 1.0 pairs
+    for (int i = threadIdx.x; i < 512; i += NTHREADS) reinterpret_cast<uint32_t *>(sOnes)[i] = 0x3F803F80u;  // bf16 1.0 pairs
     fence_proxy_async_smem();
   }
   if (warp == 1) tmem_alloc_g<CTAS, TMEM_COLS>(tmem_slot);
@@ -305,7 +311,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       uint32_t it = 0;
       for (int item = unit; item < n_items; item += n_units) {
         const int t = item % n_tiles, sp = item / n_tiles;
-        const int m0 = ((t % tiles_m) * CTAS + (int)rank) * BM, n0 = (t / tiles_m) * BN + (int)rank * BNL;
+        const int tmi = g.n_fast ? t / tiles_n : t % tiles_m, tni = g.n_fast ? t % tiles_n : t / tiles_m;
+        const int m0 = (tmi * CTAS + (int)rank) * BM, n0 = tni * BN + (int)rank * BNL;
         const int ks0 = sp * kps, ks1 = min(k_steps, ks0 + kps);
         for (int ks = ks0; ks < ks1; ++ks, ++it) {
           const int s = it % STAGES;
@@ -355,7 +362,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       uint32_t it = 0, tl = 0;
       for (int item = unit; item < n_items; item += n_units, ++tl) {
         const int t = item % n_tiles, sp = item / n_tiles;
-        const bool bias_tile = with_bias_grad && (t / tiles_m) == 0;
+        const bool bias_tile = with_bias_grad && (g.n_fast ? t % tiles_n : t / tiles_m) == 0;
         const int ks0 = sp * kps, ks1 = min(k_steps, ks0 + kps);
         const int b = tl % ACC_BUFS;
         mbar_wait(acc_empty + b, ((tl / ACC_BUFS) & 1u) ^ 1u);  // every epilogue warp of the unit drained this accumulator
@@ -379,41 +386,44 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       }
     }
   } else {
-    // ------------------------------- epilogue (warps 2..9) -------------------------------
-    // Two warps per TMEM lane quadrant, each taking half of the tile's columns.  Per tile the bias slice is staged once in
-    // shared memory (double-buffered with the accumulator), TMEM loads run one 32-column chunk ahead of the math.
+    // ------------------------------- epilogue (warps 2..13) -------------------------------
+    // Three warps per TMEM lane quadrant; chunk c (32 columns) of the tile belongs to warp part c % 3.  Per tile the bias
+    // slice is staged once in shared memory (double-buffered), TMEM loads run one chunk ahead of the math.
     const int q = warp & 3;             // TMEM lane quadrant this warp may access (hardware rule: warp id % 4)
-    const int half = (warp - 2) >> 2;   // which half of the BN columns
-    const int et = threadIdx.x - 64;    // 0..255
+    const int part = (warp - 2) >> 2;   // 0..2
+    const int et = threadIdx.x - 64;    // 0..383
     const int row_in_tile = q * 32 + lane;
-    constexpr int NCHUNK = BN / 64;     // 32-column chunks per warp
+    constexpr int NCH = BN / 32;        // 32-column chunks of the tile
     uint8_t *stg = reinterpret_cast<uint8_t *>(stage) + (warp - 2) * STG_BYTES;
     const unsigned long long seed = (EPI != EPI_WGRAD && g.t16) ? attn::effective_seed(g.seed, g.seed_offset) : 0ull;
     uint32_t tl = 0;
     for (int item = unit; item < n_items; item += n_units, ++tl) {
       const int t = item % n_tiles;
       const int b = tl % ACC_BUFS;
-      const int m0 = ((t % tiles_m) * CTAS + (int)rank) * BM, n0 = (t / tiles_m) * BN;
+      const int tmi = g.n_fast ? t / tiles_n : t % tiles_m, tni = g.n_fast ? t % tiles_n : t / tiles_m;
+      const int m0 = (tmi * CTAS + (int)rank) * BM, n0 = tni * BN;
       const int row = m0 + row_in_tile;
       const int wrow0 = m0 + q * 32;  // first accumulator row of this warp
       float *sb = sbias + (tl & 1) * BN;
       if (EPI == EPI_FWD) {
         if (et < BN) sb[et] = (g.bias != nullptr && n0 + et < g.N) ? __ldg(g.bias + n0 + et) : 0.f;
-        asm volatile("bar.sync 1, 256;" ::: "memory");  // bias visible; everybody is done with the tile before last
+        asm volatile("bar.sync 1, 384;" ::: "memory");  // bias visible; everybody is done with the tile before last
       }
       uint32_t rk = 0;
       if (EPI != EPI_WGRAD && g.t16) rk = attn::drop_row_key(seed, (unsigned long long)row);
       mbar_wait(acc_full + b, (tl / ACC_BUFS) & 1u);
       fence_after_sync();
-      const uint32_t taddr = tmem + b * BN + half * (BN / 2) + ((uint32_t)(q * 32) << 16);
+      const uint32_t taddr = tmem + b * BN + ((uint32_t)(q * 32) << 16);
       uint32_t rr[2][32];
-      tmem_ld32_async(taddr, rr[0]);
+      if (part < NCH) tmem_ld32_async(taddr + part * 32, rr[0]);
 #pragma unroll
-      for (int ci = 0; ci < NCHUNK; ++ci) {
-        uint32_t(&cur)[32] = rr[ci & 1];
+      for (int cj = 0; cj < (NCH + EPI_PARTS - 1) / EPI_PARTS; ++cj) {
+        const int ci = part + cj * EPI_PARTS;
+        if (ci >= NCH) break;
+        uint32_t(&cur)[32] = rr[cj & 1];
         tmem_wait32(cur);
-        if (ci + 1 < NCHUNK) tmem_ld32_async(taddr + (ci + 1) * 32, rr[(ci + 1) & 1]);
-        const int c0 = half * (BN / 2) + ci * 32;
+        if (ci + EPI_PARTS < NCH) tmem_ld32_async(taddr + (ci + EPI_PARTS) * 32, rr[(cj + 1) & 1]);
+        const int c0 = ci * 32;
         const int col0 = n0 + c0;
         if (col0 < g.N) {
           float v[32];
@@ -520,7 +530,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
           }
         }
       }
-      if (EPI == EPI_WGRAD && with_bias_grad && n0 == 0 && half == 0) {
+      if (EPI == EPI_WGRAD && with_bias_grad && n0 == 0 && part == 0) {
         // every column of the N = 16 ones-product equals sum_k A[row][k]: the bias gradient of output feature `row`
         uint32_t r16[16];
         attn::tmem_ld16_async(tmem + ACC_COLS + b * 32 + ((uint32_t)(q * 32) << 16), r16);
@@ -604,11 +614,11 @@ int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mb, const GemmArgs &g,
   const int max_units = sms / CTAS;
   const int grid = (units < max_units ? units : max_units) * CTAS;
   if (CTAS == 1) {
-    kern<<<grid, 320, smem, st>>>(ma, mb, g);
+    kern<<<grid, NTHREADS, smem, st>>>(ma, mb, g);
   } else {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(320);
+    cfg.blockDim = dim3(NTHREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -675,6 +685,9 @@ int run_gemm(int epi, const void *A, int lda, int a_t, const void *B, int ldb, i
   if (sms == 0) return SV_ERR_INVALID_ARG;
   g.a_mn = a_t ? 1 : 0;
   g.b_mn = b_t ? 1 : 0;
+  // the operand with the SMALLER footprint is the one re-read across the in-flight tiles (it stays in L2); the larger one
+  // is streamed from HBM exactly once
+  g.n_fast = (long long)N <= (long long)M ? 1 : 0;
   // CTA pairs (M = 256 per MMA) whenever there are at least two 128-row tiles and enough work to fill the pairs
   int ctas = (M > BM && (long long)M * N >= 256ll * 128 * (sms / 2)) ? 2 : 1;
   if (g_force_ctas == 1 || g_force_ctas == 2) ctas = (g_force_ctas == 2 && M > BM) ? 2 : 1;

@@ -236,19 +236,20 @@ class _LinearFn(torch.autograd.Function):
         Np = _round8(N)
         assert act is None or Np == N
         M = x2.shape[0]
-        out = torch.empty((M, Np), dtype=torch.bfloat16, device=x.device)
+        y = torch.empty((*x.shape[:-1], Np), dtype=torch.bfloat16, device=x.device)   # returned as is: not a view
+        out = y.view(M, Np)
         if Np != N:
             out[:, N:].zero_()
         need_grad = any(ctx.needs_input_grad[:3])
         pre = None
         if act == "gelu" and need_grad:
-            out, pre = native.linear_fwd(x2, wb, _f32(bias), act, out=out, n_out=N, want_pre=True)
+            _, pre = native.linear_fwd(x2, wb, _f32(bias), act, out=out, n_out=N, want_pre=True)
         else:
             native.linear_fwd(x2, wb, _f32(bias), act, out=out, n_out=N)
-        ctx.save_for_backward(x2, wb, out if act == "relu" else pre)
+        ctx.save_for_backward(x2, wb, out.detach() if act == "relu" else pre)
         ctx.params = (weight, bias)
         ctx.meta = (x.shape, x.dtype, act, N, K)
-        return out.view(*x.shape[:-1], Np)
+        return y
 
     @staticmethod
     def backward(ctx, g):
@@ -290,11 +291,12 @@ class _FFNFn(torch.autograd.Function):
             h, pre = native.linear_fwd(x2, wb1, _f32(b1), act, dropout_p=p, seed=seed, want_pre=True)
         else:
             h = native.linear_fwd(x2, wb1, _f32(b1), act, dropout_p=p, seed=seed)
-        y = native.linear_fwd(h, wb2, _f32(b2))
+        y = torch.empty((*x.shape[:-1], N), dtype=torch.bfloat16, device=x.device)
+        native.linear_fwd(h, wb2, _f32(b2), out=y.view(-1, N))
         ctx.save_for_backward(x2, wb1, wb2, h, pre)
         ctx.params = (w1, b1, w2, b2)
         ctx.meta = (x.shape, x.dtype, act, p, seed)
-        return y.view(*x.shape[:-1], N)
+        return y
 
     @staticmethod
     def backward(ctx, g):
@@ -334,10 +336,11 @@ class _PackedLinearFn(torch.autograd.Function):
             bias = torch.cat([b.detach().float() for b in bs], 0)
         K = wb.shape[1]
         x2 = _rows_bf16(x, K)
-        out = native.linear_fwd(x2, wb, bias)
+        y = torch.empty((*x.shape[:-1], wb.shape[0]), dtype=torch.bfloat16, device=x.device)
+        native.linear_fwd(x2, wb, bias, out=y.view(-1, wb.shape[0]))
         ctx.save_for_backward(x2, wb)
         ctx.params, ctx.pack, ctx.meta = params, pack, (x.shape, x.dtype)
-        return out.view(*x.shape[:-1], wb.shape[0])
+        return y
 
     @staticmethod
     def backward(ctx, g):

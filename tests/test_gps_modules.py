@@ -301,7 +301,7 @@ def test_graph_step_matches_eager_step_parameters():
         # the first AdamW step moves a coordinate by -lr * g / (|g| + eps): same sign and (almost) the same size in both paths
         agree = (torch.sign(de[big]) == torch.sign(dg[big])).float().mean().item()
         ratio = (dg[big].abs().mean() / (de[big].abs().mean() + 1e-20)).item()
-        worst = min(worst, (agree, n))
+        worst = min(worst, (agree, n), key=lambda t: t[0])
         checked += 1
         assert agree > 0.98 and 0.9 < ratio < 1.1, (n, agree, ratio)
     assert checked > 100, checked

