@@ -53,6 +53,11 @@ int sv_gemm_bf16_ex(const void *A, int lda, int a_transposed, const void *B, int
                     const float *bias, int act, const void *residual, void *out, int ldo, int out_f32, int rowmax,
                     void *stream);
 
+/* Micro-benchmark (profiling only): SM cycles for `iters` x 4 tcgen05.mma (M = 128, N, K = 16 each) issued back to back on
+ * shared-memory-resident operands, per block, by operand layout (a_mn / b_mn = 1: MN-major, transposed operand).
+ * cycles_out: `blocks` int64 on the device. */
+int sv_mma_bench(int N, int a_mn, int b_mn, int iters, int blocks, long long *cycles_out, void *stream);
+
 /* Kernel selection of the GEMM family (tests / benchmarks): 0 = heuristic (default), 1 = single-CTA tiles (M = 128 per MMA),
  * 2 = CTA pairs (cta_group::2, M = 256 per MMA, each CTA stages half of the B tile) wherever M > 128. */
 int sv_gemm_force_ctas(int ctas);
@@ -150,6 +155,10 @@ int sv_layer_norm_fwd(const void *x, const void *residual, int io_bf16, int R, i
 int sv_layer_norm_bwd(const void *g, const void *s, int io_bf16, int R, int D, const float *gamma, const float *mean,
                       const float *rstd, float dropout_p, unsigned long long seed, void *ds, void *dx, float *dgamma,
                       float *dbeta, float *scratch, void *stream);
+/* same; accumulate = 1 adds dgamma / dbeta into the given buffers (the flat gradient buffer) instead of overwriting them */
+int sv_layer_norm_bwd_acc(const void *g, const void *s, int io_bf16, int R, int D, const float *gamma, const float *mean,
+                          const float *rstd, float dropout_p, unsigned long long seed, void *ds, void *dx, float *dgamma,
+                          float *dbeta, int accumulate, float *scratch, void *stream);
 int sv_layer_norm_scratch_floats(int D);
 
 /* Every in-kernel dropout mask (attention weights, fused LayerNorm) is a pure function of (seed, indices).  A captured

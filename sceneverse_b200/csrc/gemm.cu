@@ -638,27 +638,44 @@ int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mb, const GemmArgs &g,
   return sv::after_launch();
 }
 
-// Tile width: the persistent grid runs ceil(tiles / units) waves, so the cheapest width is the one whose LAST wave is
-// fullest; relative cost of one tile by width (MMA time + the fixed per-tile overhead; narrow tiles are operand-bandwidth
-// bound).  `mn_b`: B is a transposed (MN-major) operand staged in 64-column slabs, so a CTA pair needs BN / 2 % 64 == 0.
-int pick_bn(int M, int N, int units, int ctas, bool allow256, bool mn_b) {
+// Tile selection.  ncu + the layout micro-benchmark (profiles/r2_gemm_ncu_summary.json, r2_mma_bench.json) show the main loop
+// bounded by SHARED-MEMORY traffic, not by the tensor pipe or L2: every K step the TMA writes the stage (A: 16 KB, B:
+// 128 B x the rows this CTA stages) and the tensor core reads it back (A: 16 KB, B: all BN rows, half of them from the peer
+// CTA in pair mode) at ~108 B/clk combined, against 2 x BN clk of math.  Cost of one tile = max(math, traffic / 108); the
+// persistent grid runs ceil(tiles / units) waves of it.  `mn_b`: B is a transposed (MN-major) operand staged in 64-column
+// slabs, so a CTA pair needs BN / 2 % 64 == 0.
+float tile_cost(int bn, int ctas) {
+  const float math = 2.0f * bn;
+  const float wr = 16384.f + 128.f * bn / ctas, rd = 16384.f + 128.f * bn;
+  const float mem = (wr + rd) / 108.f;
+  return math > mem ? math : mem;
+}
+
+void pick_tile(int M, int N, int sms, bool mn_b, bool allow_pair, int force_ctas, bool wgrad, int *bn_out, int *ctas_out) {
   const int cand[4] = {256, 192, 128, 64};
-  const float w[4] = {1.00f, 0.78f, 0.56f, 0.34f};
-  int best = 0;
   float best_cost = 1e30f;
-  const int tm = (M + ctas * BM - 1) / (ctas * BM);
-  for (int i = 0; i < 4; ++i) {
-    if (cand[i] == 256 && !allow256) continue;
-    if (ctas == 2 && mn_b && (cand[i] / 2) % 64) continue;
-    if (ctas == 2 && cand[i] == 64) continue;
-    const int tiles = tm * ((N + cand[i] - 1) / cand[i]);
-    const float cost = (float)((tiles + units - 1) / units) * w[i];
-    if (cost < best_cost - 1e-6f) {
-      best_cost = cost;
-      best = cand[i];
+  *bn_out = 64;
+  *ctas_out = 1;
+  for (int ctas = 1; ctas <= 2; ++ctas) {
+    if (force_ctas && ctas != force_ctas && !(force_ctas == 2 && M <= BM && ctas == 1)) continue;
+    if (ctas == 2 && (!allow_pair || M <= BM)) continue;
+    const int units = sms / ctas;
+    const int tm = (M + ctas * BM - 1) / (ctas * BM);
+    for (int i = 0; i < 4; ++i) {
+      const int bn = cand[i];
+      if (ctas == 2 && (bn == 64 || (mn_b && (bn / 2) % 64))) continue;
+      if (bn > 64 && bn - 64 >= ((N + 63) / 64) * 64) continue;          // wider than the problem by a whole 64-column slab
+      const int tiles = tm * ((N + bn - 1) / bn);
+      // a weight gradient fills the machine through split-K, so only the per-area cost of the tile matters there
+      const float waves = wgrad ? (float)tiles / units : (float)((tiles + units - 1) / units);
+      const float cost = waves * tile_cost(bn, ctas);
+      if (cost < best_cost * 0.999f) {
+        best_cost = cost;
+        *bn_out = bn;
+        *ctas_out = ctas;
+      }
     }
   }
-  return best;
 }
 
 template <int EPI, int CTAS>
@@ -688,13 +705,9 @@ int run_gemm(int epi, const void *A, int lda, int a_t, const void *B, int ldb, i
   // the operand with the SMALLER footprint is the one re-read across the in-flight tiles (it stays in L2); the larger one
   // is streamed from HBM exactly once
   g.n_fast = (long long)N <= (long long)M ? 1 : 0;
-  // CTA pairs (M = 256 per MMA) whenever there are at least two 128-row tiles and enough work to fill the pairs
-  int ctas = (M > BM && (long long)M * N >= 256ll * 128 * (sms / 2)) ? 2 : 1;
-  if (g_force_ctas == 1 || g_force_ctas == 2) ctas = (g_force_ctas == 2 && M > BM) ? 2 : 1;
-  if (g.rowmax) ctas = 1;
+  int bn = 64, ctas = 1;
+  pick_tile(M, N, sms, b_t != 0, g.rowmax == 0, g_force_ctas, epi == EPI_WGRAD, &bn, &ctas);
   const int units = sms / ctas;
-  const int bn = pick_bn(M, N, units, ctas, true, b_t != 0);
-  if (bn == 0) return SV_ERR_INVALID_ARG;
   g.splits = 1;
   if (epi == EPI_WGRAD && g.red_out) {
     // split-K: the output of a weight gradient is small (a few dozen tiles), the contraction runs over every token

@@ -250,7 +250,8 @@ __global__ void __launch_bounds__(512) ln_bwd_dgb_kernel(const LnArgs a) {
 }
 
 // backward, part 3: fixed-order sum of the per-CTA partials; one CTA per 32 columns, the 8 warps split the partial rows
-__global__ void __launch_bounds__(256) ln_bwd_reduce_kernel(const float *partials, int nblk, int D, float *dgamma, float *dbeta) {
+__global__ void __launch_bounds__(256) ln_bwd_reduce_kernel(const float *partials, int nblk, int D, float *dgamma, float *dbeta,
+                                                           int accumulate) {
   __shared__ float red[8][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int d = blockIdx.x * 32 + lane;
@@ -263,7 +264,8 @@ __global__ void __launch_bounds__(256) ln_bwd_reduce_kernel(const float *partial
     float t = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) t += red[w][lane];
-    if (d < D) dgamma[d] = t; else dbeta[d - D] = t;
+    float *dst = d < D ? dgamma + d : dbeta + (d - D);
+    *dst = accumulate ? *dst + t : t;   // accumulate: straight into the flat gradient buffer (one writer per element)
   }
 }
 
@@ -280,7 +282,7 @@ int launch_fwd(const LnArgs &a, bool has_res, bool drop, cudaStream_t st) {
   return sv::after_launch();
 }
 template <typename T, int MAXCH>
-int launch_bwd(const LnArgs &a, bool drop, float *dgamma, float *dbeta, cudaStream_t st) {
+int launch_bwd(const LnArgs &a, bool drop, float *dgamma, float *dbeta, int accumulate, cudaStream_t st) {
   int grid = (a.R + 7) / 8;
   if (grid > 148 * 8) grid = 148 * 8;
   if (drop) ln_bwd_dx_kernel<T, MAXCH, true><<<grid, 256, 0, st>>>(a);
@@ -294,7 +296,7 @@ int launch_bwd(const LnArgs &a, bool drop, float *dgamma, float *dbeta, cudaStre
   ln_bwd_dgb_kernel<T><<<nblk, block, (size_t)DGB_ROWS * 2 * a.D * sizeof(float), st>>>(a);
   rc = sv::after_launch();
   if (rc) return rc;
-  ln_bwd_reduce_kernel<<<(2 * a.D + 31) / 32, 256, 0, st>>>(a.partials, nblk, a.D, dgamma, dbeta);
+  ln_bwd_reduce_kernel<<<(2 * a.D + 31) / 32, 256, 0, st>>>(a.partials, nblk, a.D, dgamma, dbeta, accumulate);
   return sv::after_launch();
 }
 
@@ -340,6 +342,12 @@ extern "C" int sv_layer_norm_fwd(const void *x, const void *residual, int io_bf1
 extern "C" int sv_layer_norm_bwd(const void *g, const void *s, int io_bf16, int R, int D, const float *gamma,
                                  const float *mean, const float *rstd, float dropout_p, unsigned long long seed, void *ds,
                                  void *dx, float *dgamma, float *dbeta, float *scratch, void *stream) {
+  return sv_layer_norm_bwd_acc(g, s, io_bf16, R, D, gamma, mean, rstd, dropout_p, seed, ds, dx, dgamma, dbeta, 0, scratch, stream);
+}
+
+extern "C" int sv_layer_norm_bwd_acc(const void *g, const void *s, int io_bf16, int R, int D, const float *gamma,
+                                     const float *mean, const float *rstd, float dropout_p, unsigned long long seed, void *ds,
+                                     void *dx, float *dgamma, float *dbeta, int accumulate, float *scratch, void *stream) {
   if (R < 1 || D < 8 || (D % 8) || D > 1024 || !(dropout_p >= 0.f) || dropout_p >= 1.f) return SV_ERR_INVALID_ARG;
   const bool drop = dropout_p > 0.f;
   if (!g || !s || !gamma || !mean || !rstd || !ds || !dgamma || !dbeta || !scratch || (drop && !dx)) return SV_ERR_INVALID_ARG;
@@ -353,16 +361,16 @@ extern "C" int sv_layer_norm_bwd(const void *g, const void *s, int io_bf16, int 
   const bool d = a.t16 != 0;
   if (io_bf16) {
     switch (maxch) {
-      case 1: return launch_bwd<__nv_bfloat16, 1>(a, d, dgamma, dbeta, st);
-      case 2: return launch_bwd<__nv_bfloat16, 2>(a, d, dgamma, dbeta, st);
-      case 3: return launch_bwd<__nv_bfloat16, 3>(a, d, dgamma, dbeta, st);
-      default: return launch_bwd<__nv_bfloat16, 4>(a, d, dgamma, dbeta, st);
+      case 1: return launch_bwd<__nv_bfloat16, 1>(a, d, dgamma, dbeta, accumulate, st);
+      case 2: return launch_bwd<__nv_bfloat16, 2>(a, d, dgamma, dbeta, accumulate, st);
+      case 3: return launch_bwd<__nv_bfloat16, 3>(a, d, dgamma, dbeta, accumulate, st);
+      default: return launch_bwd<__nv_bfloat16, 4>(a, d, dgamma, dbeta, accumulate, st);
     }
   }
   switch (maxch) {
-    case 1: return launch_bwd<float, 1>(a, d, dgamma, dbeta, st);
-    case 2: return launch_bwd<float, 2>(a, d, dgamma, dbeta, st);
-    case 3: return launch_bwd<float, 3>(a, d, dgamma, dbeta, st);
-    default: return launch_bwd<float, 4>(a, d, dgamma, dbeta, st);
+    case 1: return launch_bwd<float, 1>(a, d, dgamma, dbeta, accumulate, st);
+    case 2: return launch_bwd<float, 2>(a, d, dgamma, dbeta, accumulate, st);
+    case 3: return launch_bwd<float, 3>(a, d, dgamma, dbeta, accumulate, st);
+    default: return launch_bwd<float, 4>(a, d, dgamma, dbeta, accumulate, st);
   }
 }

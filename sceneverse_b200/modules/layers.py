@@ -29,11 +29,23 @@ class Linear(nn.Linear):
         return ops.linear(x, self.weight, self.bias)
 
 
+class Embedding(nn.Embedding):
+    """nn.Embedding (same parameters / state_dict) whose backward is the native scatter-add (ops.embedding)."""
+
+    def forward(self, ids):
+        if self.max_norm is not None or self.sparse or self.scale_grad_by_freq:
+            return super().forward(ids)
+        return ops.embedding(ids, self.weight, self.padding_idx)
+
+
 def route_linears(module):
-    """Re-class every plain nn.Linear below `module` (incl. third-party sub-modules such as the HF BERT blocks)."""
+    """Re-class every plain nn.Linear / nn.Embedding below `module` (incl. third-party sub-modules such as the HF BERT
+    blocks) so that their arithmetic goes through sceneverse_b200.ops."""
     for m in module.modules():
         if type(m) is nn.Linear:
             m.__class__ = Linear
+        elif type(m) is nn.Embedding:
+            m.__class__ = Embedding
     return module
 
 

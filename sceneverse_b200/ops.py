@@ -368,6 +368,48 @@ def linear_packed(x, linears):
     return torch.cat([linear(x, l.weight, l.bias) for l in linears], dim=-1)
 
 
+class _EmbeddingFn(torch.autograd.Function):
+    """nn.Embedding lookup whose backward is ONE native scatter-add (csrc/train_ops.cu embedding_bwd_kernel, fp32 red.add)
+    instead of ATen's sort + segmented reduction (8 kernels); tiny tables (token types) use masked column sums, where every
+    row would hit the same few addresses."""
+
+    @staticmethod
+    def forward(ctx, ids, weight, padding_idx):
+        ctx.save_for_backward(ids)
+        ctx.weight, ctx.padding_idx = weight, padding_idx
+        return F.embedding(ids, weight, padding_idx)
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import native
+        (ids,) = ctx.saved_tensors
+        weight, pad = ctx.weight, ctx.padding_idx
+        direct = _direct(weight)
+        dw = weight.grad if direct else torch.zeros_like(weight, dtype=torch.float32)
+        g2 = g.reshape(-1, g.shape[-1])
+        if weight.shape[0] <= 4:
+            flat = ids.reshape(-1)
+            total = native.colsum(g2 if g2.dtype in (torch.bfloat16, torch.float32) else g2.float())
+            rest = torch.zeros_like(total)
+            for v in range(1, weight.shape[0]):
+                if pad is not None and v == pad:
+                    continue
+                part = native.colsum((g2 * (flat == v).unsqueeze(1).to(g2.dtype)).contiguous())
+                dw[v] += part
+                rest += part
+            if pad is None or pad != 0:
+                dw[0] += total - rest
+        else:
+            native.embedding_bwd(g2, ids, dw, padding_idx=-1 if pad is None else pad)
+        return None, (None if direct else dw), None
+
+
+def embedding(ids, weight, padding_idx=None):
+    if weight.is_cuda and weight.dtype == torch.float32 and torch.is_grad_enabled() and weight.requires_grad and ids.dtype == torch.int64:
+        return _EmbeddingFn.apply(ids, weight, padding_idx)
+    return F.embedding(ids, weight, padding_idx)
+
+
 def _native_linear_ok(x, weight):
     return x.is_cuda and weight.is_cuda and weight.dim() == 2 and x.numel() > 0 and weight.dtype in (torch.float32, torch.bfloat16) \
         and (x.dtype == torch.bfloat16 or _autocast_on())
@@ -521,12 +563,19 @@ class _CrossEntropyFn(torch.autograd.Function):
         # same validity predicate as the kernel: a label outside [0, V) that is not ignore_index contributes nothing
         count = ((labels != ignore_index) & (labels >= 0) & (labels < V)).sum().float()
         ctx.save_for_backward(grad, count)
+        ctx.scaled = False
         return loss_rows.sum() / count        # every row ignored: 0 / 0 = nan, like torch
 
     @staticmethod
     def backward(ctx, gout):
         grad, count = ctx.saved_tensors
-        return grad * (gout / count).to(grad.dtype), None, None, None
+        # the (R, V) gradient (195 MB for the LM head) is scaled IN PLACE: one pass instead of a second 195 MB tensor; a
+        # second backward through the same node (retain_graph) would scale it twice, so it is refused
+        if ctx.scaled:
+            raise RuntimeError("ops.cross_entropy: backward through the same graph twice is not supported (the saved "
+                               "gradient buffer is consumed in place)")
+        ctx.scaled = True
+        return grad.mul_((gout / count).to(grad.dtype)), None, None, None
 
 
 def padded_vocab_linear(h, weight, bias):
@@ -568,6 +617,7 @@ class _LayerNormFn(torch.autograd.Function):
         _lib.check(lib, st, "sv_layer_norm_fwd")
         ctx.save_for_backward(s if need_s else x2, gamma, stats)
         ctx.meta = (float(p), int(seed), residual is not None, x.shape)
+        ctx.params = (gamma, beta)
         return y.view(x.shape)
 
     @staticmethod
@@ -579,17 +629,21 @@ class _LayerNormFn(torch.autograd.Function):
         g2 = g.reshape(R, D).to(s.dtype).contiguous()
         ds = torch.empty_like(s)
         dx = torch.empty_like(s) if p > 0.0 else None
-        dgb = torch.empty((2, D), dtype=torch.float32, device=s.device)
+        pg, pb = ctx.params
+        direct = _direct(pg) and _direct(pb)        # gamma / beta gradients accumulate straight into the flat buffer
+        dgb = None if direct else torch.empty((2, D), dtype=torch.float32, device=s.device)
+        dg_t, db_t = (pg.grad, pb.grad) if direct else (dgb[0], dgb[1])
         lib = _lib.gps()
         scratch = torch.empty(lib.sv_layer_norm_scratch_floats(D), dtype=torch.float32, device=s.device)
         with torch.cuda.device(s.device):
-            st = lib.sv_layer_norm_bwd(g2.data_ptr(), s.data_ptr(), 1 if s.dtype == torch.bfloat16 else 0, R, D,
-                                       gamma.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(), p, seed, ds.data_ptr(),
-                                       dx.data_ptr() if dx is not None else None, dgb[0].data_ptr(), dgb[1].data_ptr(),
-                                       scratch.data_ptr(), torch.cuda.current_stream(s.device).cuda_stream)
-        _lib.check(lib, st, "sv_layer_norm_bwd")
+            st = lib.sv_layer_norm_bwd_acc(g2.data_ptr(), s.data_ptr(), 1 if s.dtype == torch.bfloat16 else 0, R, D,
+                                           gamma.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(), p, seed, ds.data_ptr(),
+                                           dx.data_ptr() if dx is not None else None, dg_t.data_ptr(), db_t.data_ptr(),
+                                           1 if direct else 0, scratch.data_ptr(),
+                                           torch.cuda.current_stream(s.device).cuda_stream)
+        _lib.check(lib, st, "sv_layer_norm_bwd_acc")
         d_x = (dx if dx is not None else ds).view(shape)
-        return d_x, (ds.view(shape) if has_res else None), dgb[0], dgb[1], None, None, None
+        return d_x, (ds.view(shape) if has_res else None), (None if direct else dgb[0]), (None if direct else dgb[1]), None, None, None
 
 
 def _autocast_on():

@@ -322,9 +322,13 @@ def test_linear_fn_matches_autocast_linear():
     assert W.grad.dtype == torch.float32 and b.grad.dtype == torch.float32 and x.grad.dtype == torch.float32
     for t in (x, W, b):
         t.grad = None
-    with torch.autocast("cuda", dtype=torch.bfloat16):
-        yr = F.relu(F.linear(x, W, b))
-    yr.backward(go.bfloat16())
-    for g, w, name in zip(got, (yr.detach().float(), x.grad, W.grad, b.grad), "yxWb"):
+    # fp32 reference on the bf16-rounded operands (torch's own bf16 GEMMs may reduce in bf16:
+    # torch.backends.cuda.matmul.allow_bf16_reduced_precision_reduction)
+    xr = x.detach().bfloat16().float().requires_grad_(True)
+    Wr = W.detach().bfloat16().float().requires_grad_(True)
+    br = b.detach().clone().requires_grad_(True)
+    yr = F.relu(F.linear(xr, Wr, br))
+    yr.backward(go.bfloat16().float())
+    for g, w, name in zip(got, (yr.detach().float(), xr.grad, Wr.grad, br.grad), "yxWb"):
         err = (g - w).abs().max().item() / (w.abs().max().item() + 1e-9)
         assert err < 1e-2, (name, err)

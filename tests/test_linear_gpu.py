@@ -144,7 +144,7 @@ def test_ops_ffn_autograd_matches_torch(act, p, H):
     yr = F.linear(h, ps[2].bfloat16().float(), ps[3])
     yr.backward(go.float())
     assert rel(y, yr) < 1e-2
-    assert rel(x.grad, xf.grad) < 1.5e-2
+    assert rel(x.grad, xf.grad) < 3e-2       # dL/dpre passes through bf16 between the two dgrad GEMMs
     for got, want, name in zip((w1.grad, b1.grad, w2.grad, b2.grad), ps, ("w1", "b1", "w2", "b2")):
         assert rel(got, want.grad) < 1.5e-2, name
 
@@ -199,3 +199,15 @@ def test_linear_packed_and_attention_packed_match_the_unpacked_path():
     want = [ref.detach(), x.grad] + [p.grad for l in lins for p in (l.weight, l.bias)]
     for g, w, name in zip(got, want, ["out", "dx", "dWq", "dbq", "dWk", "dbk", "dWv", "dbv"]):
         assert rel(g, w) < 1e-2, name
+
+
+@pytest.mark.parametrize("V,pad", [(1000, 0), (2, None), (512, None)])
+def test_ops_embedding_autograd_matches_torch(V, pad):
+    from sceneverse_b200 import ops
+    ids = torch.randint(0, V, (64, 50), device="cuda")
+    w = rnd(V, 768).requires_grad_(True)
+    go = rnd(64, 50, 768, seed=3)
+    ops.embedding(ids, w, pad).backward(go)
+    wr = w.detach().clone().requires_grad_(True)
+    F.embedding(ids, wr, pad).backward(go)
+    assert rel(w.grad, wr.grad) < 1e-5
