@@ -196,6 +196,10 @@ int sv_cross_entropy_fwd_bwd_strided(const void *logits, long long row_stride, i
 int sv_act_bwd_bf16(const void *g, int ldg, const void *aux, int ld_aux, int mode, int M, int N, void *out, int ldo,
                     void *stream);
 
+/* x[0..n) *= *scale (device scalar) in place, bf16 | f32, n % (8 | 4) == 0, 16-byte aligned: the 1/count scaling of the fused
+ * cross-entropy gradient without a second (R, V) tensor. */
+int sv_scale_inplace(void *x, long long n, int is_bf16, const float *scale, void *stream);
+
 /* Gradient of an embedding lookup: dw[ids[t]][:] += grad_out[t][:] (fp32 red.add; rows with ids == padding_idx skipped).
  * grad_out (ntok, D) bf16 | f32 with row stride ldg; dw (vocab, D) f32 contiguous, NOT zeroed here (accumulates).
  * (reference: autograd of the three nn.Embedding tables of HF BertEmbeddings, modules/language/bert.py:21-26) */

@@ -79,6 +79,25 @@ __global__ void __launch_bounds__(256) embedding_bwd_kernel(const T *g, long lon
   }
 }
 
+// x *= *scale (device scalar), 8 bf16 / 4 f32 per thread: the in-place 1/count scaling of the cross-entropy gradient
+template <typename T>
+__global__ void __launch_bounds__(256) scale_inplace_kernel(T *x, long long n16, const float *scale) {
+  const float s = __ldg(scale);
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n16; i += (long long)gridDim.x * 256) {
+    uint4 v = reinterpret_cast<uint4 *>(x)[i];
+    uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (sizeof(T) == 2) {
+        w[k] = tc05::pack_bf16(__uint_as_float(w[k] << 16) * s, __uint_as_float(w[k] & 0xFFFF0000u) * s);
+      } else {
+        w[k] = __float_as_uint(__uint_as_float(w[k]) * s);
+      }
+    }
+    reinterpret_cast<uint4 *>(x)[i] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
 struct AdamSeg {          // one parameter group slice of the flat buffer: [begin, end) in elements (multiples of 4)
   long long begin, end;
   float lr_scale;         // base lr of the group / reference lr (the device lr word holds the schedule factor)
@@ -195,6 +214,18 @@ extern "C" int sv_embedding_bwd(const void *grad_out, long long ldg, int is_bf16
   else
     embedding_bwd_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float *)grad_out, ldg, ids, dw, ntok, D, vocab,
                                                                         padding_idx);
+  return sv::after_launch();
+}
+
+extern "C" int sv_scale_inplace(void *x, long long n, int is_bf16, const float *scale, void *stream) {
+  if (n < 0 || !scale) return SV_ERR_INVALID_ARG;
+  if (n == 0) return SV_OK;
+  const long long per = is_bf16 ? 8 : 4;
+  if (!x || (n % per) || (reinterpret_cast<uintptr_t>(x) & 15)) return SV_ERR_INVALID_ARG;
+  const long long n16 = n / per;
+  const int grid = (int)((n16 + 255) / 256 < 148 * 16 ? (n16 + 255) / 256 : 148 * 16);
+  if (is_bf16) scale_inplace_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16 *)x, n16, scale);
+  else scale_inplace_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((float *)x, n16, scale);
   return sv::after_launch();
 }
 

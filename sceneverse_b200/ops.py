@@ -575,7 +575,16 @@ class _CrossEntropyFn(torch.autograd.Function):
             raise RuntimeError("ops.cross_entropy: backward through the same graph twice is not supported (the saved "
                                "gradient buffer is consumed in place)")
         ctx.scaled = True
-        return grad.mul_((gout / count).to(grad.dtype)), None, None, None
+        scale = (gout.float() / count).reshape(1).contiguous()
+        if grad.is_contiguous() and grad.numel() % 8 == 0 and grad.data_ptr() % 16 == 0:
+            from . import _lib
+            lib = _lib.gps()
+            with torch.cuda.device(grad.device):
+                st = lib.sv_scale_inplace(grad.data_ptr(), grad.numel(), 1 if grad.dtype == torch.bfloat16 else 0,
+                                          scale.data_ptr(), torch.cuda.current_stream(grad.device).cuda_stream)
+            _lib.check(lib, st, "sv_scale_inplace")
+            return grad, None, None, None
+        return grad.mul_(scale.to(grad.dtype)), None, None, None
 
 
 def padded_vocab_linear(h, weight, bias):
