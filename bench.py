@@ -9,7 +9,12 @@ Workload (config.workload):
       bf16 autocast, data-parallel over scenes (NCCL gradient all-reduce + embedding all-gather).
       Metric: scenes/s (whole job).  `e2e` = the same step fed from pinned HOST buffers (H2D of the whole data_dict
       inside the timed region) with the loss read back.
+  scanrefer     (--workload scanrefer)     BASELINE.json configs[2]: the same encoders with GroundHeadV1 (hidden 384) and
+      og3d_loss (configs/final/finetune/scanrefer_finetune.yaml), B = 64 scenes/GPU, no scene captions.
+  objcls        (--workload objcls)        BASELINE.json configs[1]: object-level pre-training, 64 objects x 1024 points, bf16,
+      PointNet++ TRAINABLE with train-mode BatchNorm (model/objcls.py) on the native point operators (+ their gradients).
   pointops_sa1  (--workload pointops_sa1)  the FPS+ball_query front alone at the model shape (5120 x 1024), Mpts/s.
+  pointops_sweep (--workload pointops_sweep) BASELINE.json configs[4]: FPS + ball query, 16 K - 1 M points, batch 1 - 256.
 
 Every default run also measures the two gated kernels in isolation (CUDA events) and reports their rooflines:
   roofline           sa2_mlp tcgen05 kernel, tensor bound, vs measured bf16 TFLOP/s
@@ -133,7 +138,8 @@ def run_reference(args, config):
     dt = (time.perf_counter() - t0) / steps
     val = scenes / dt
     cb = {"value": val, "unit": "scenes/s", "cores": cpu_threads(), "kind": "port",
-          "sample": f"{scenes} scenes x {OBJS} objects x {PTS} pts per step (of {SCENES}), full fwd+bwd+AdamW step in fp32 on "
+          "sample": f"{scenes} scenes x {OBJS} objects x {PTS} pts per step (scenes/s extrapolated from {scenes} of the {SCENES} "
+                    "scenes of a GPU step), full fwd+bwd+AdamW step in fp32 on "
                     "CPU: sceneverse_b200 host modules + oracle/pointops_ref.c as the point-op `_ext`, torch threads = min(cores, 32)"}
     print(json.dumps({"impl": "reference", "metric": METRIC, "value": val, "unit": "scenes/s", "n_gpus": 0, "steps": steps,
                       "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -167,13 +173,30 @@ def kernel_rooflines(torch, device):
 
     t_s = timed(lambda i: _ext.fps_ballquery(xyzs[i % 3], NPOINT, RADIUS, NSAMPLE))
     ach = ALG_BYTES_PER_CLOUD * B / (t_s * 1e-3) / 1e9
+    # the meaningful "before": the reference's own CUDA kernels (sampling_gpu.cu / ball_query_gpu.cu compiled unmodified for
+    # sm_100a into oracle/_ref, measurement only) on the same clouds: FPS -> gather -> ball query, as pointnet2_modules.py:54-58
+    ref_ms = None
+    try:
+        from oracle import build_ref_ext
+        ref = build_ref_ext.load_prebuilt()
+        if ref is not None:
+            def ref_chain(i):
+                x = xyzs[i % 3]
+                idx = ref.furthest_point_sampling(x, NPOINT)
+                new = ref.gather_points(x.transpose(1, 2).contiguous(), idx).transpose(1, 2).contiguous()
+                return ref.ball_query(new, x, RADIUS, NSAMPLE)
+            ref_ms = timed(ref_chain, n=5)
+    except Exception:
+        ref_ms = None
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     tj = json.load(open(tp)) if os.path.exists(tp) else {}
     rp = {"bound": "hbm", "kernel": "sa_sample_kernel<32> (FPS + ball query, one warp per cloud)", "ms": t_s,
           "mpts_per_s": B * PTS / (t_s * 1e-3) / 1e6, "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
           "traffic": tj.get("sa_sample_kernel_dram_bytes_per_launch", traffic), "algorithmic_bytes_per_launch": ALG_BYTES_PER_CLOUD * B,
-          "peak_source": src, "note": "binding bound is fp32 instruction issue, not HBM (DESIGN.md)"}
+          "peak_source": src, "note": "binding bound is fp32 instruction issue, not HBM (DESIGN.md)",
+          "ref_cuda_ms": ref_ms, "ref_cuda_what": "reference furthest_point_sampling + gather_points (+2 transposes) + ball_query, "
+                                                  "its own sm_100a build (oracle/_ref), same 5120 x 1024 clouds"}
     net = PointNetPP(**GPS_SPEC).eval()
     net.load_state_dict(weights.synthetic_state_dict(net, 0))
     net = net.to(device)
@@ -200,13 +223,68 @@ def kernel_rooflines(torch, device):
     return rt, rp
 
 
+def attention_rooflines(torch, device):
+    """Attention kernels timed in isolation at the step's shapes (CUDA events): the attention CORE (4 B H Lq Lk 64 flops
+    forward, 2.5x that backward) and, for the language-object cross-attention of the V1 / Entity stacks, the whole block
+    projection GEMMs + core + output projection (2 (Lq + 2 Lk) D^2 + 2 Lq D^2 + 4 H Lq Lk dh per scene)."""
+    from sceneverse_b200 import native
+    _, tfl, src = peaks()
+    B, H, D = SCENES, 12, 768
+    g = torch.Generator(device=device).manual_seed(3)
+
+    def rnd(*s_):
+        return (torch.randn(*s_, device=device, generator=g) * 0.5).bfloat16()
+
+    def timed(fn, n=20):
+        for _ in range(5):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n
+    out = {"peak": tfl, "unit": "TFLOP/s", "peak_source": src, "bound": "tensor"}
+    for name, Lq, Lk in [("cross_80x50", 80, 50), ("joint_130", 130, 130), ("bert_300", 300, 300)]:
+        q, k, v = rnd(B, Lq, D), rnd(B, Lk, D), rnd(B, Lk, D)
+        go = rnd(B, Lq, D)
+        o, lse = native.attention(q, k, v, H, return_lse=True)
+        t_f = timed(lambda: native.attention(q, k, v, H, return_lse=True))
+        t_b = timed(lambda: native.attention_backward(q, k, v, o, go, lse, H))
+        fl = 4.0 * B * H * Lq * Lk * 64
+        out[name] = {"fwd_ms": t_f, "bwd_ms": t_b, "fwd_tflops": fl / (t_f * 1e-3) / 1e12, "bwd_tflops": 2.5 * fl / (t_b * 1e-3) / 1e12,
+                     "fwd_frac": fl / (t_f * 1e-3) / 1e12 / tfl, "bwd_frac": 2.5 * fl / (t_b * 1e-3) / 1e12 / tfl}
+    # cross-attention block, forward: q-projection, packed k|v projection, core, output projection — all native kernels
+    Lq, Lk = 80, 50
+    xq, xkv = rnd(B * Lq, D), rnd(B * Lk, D)
+    wq, wkv, wo = rnd(D, D), rnd(2 * D, D), rnd(D, D)
+    bq, bkv, bo = torch.zeros(D, device=device), torch.zeros(2 * D, device=device), torch.zeros(D, device=device)
+
+    def block():
+        qq = native.linear_fwd(xq, wq, bq).view(B, Lq, D)
+        kv = native.linear_fwd(xkv, wkv, bkv).view(B, Lk, 2 * D)
+        oo = native.attention(qq, kv[..., :D], kv[..., D:], H)
+        return native.linear_fwd(oo.view(B * Lq, D), wo, bo)
+    t_blk = timed(block)
+    fl_blk = B * (2.0 * (Lq + 2 * Lk) * D * D + 2.0 * Lq * D * D + 4.0 * H * Lq * Lk * 64)
+    out["cross_80x50_block"] = {"fwd_ms": t_blk, "flops": fl_blk, "fwd_tflops": fl_blk / (t_blk * 1e-3) / 1e12,
+                                "fwd_frac": fl_blk / (t_blk * 1e-3) / 1e12 / tfl,
+                                "what": "q-proj GEMM + k|v-proj GEMM + attention core + out-proj GEMM (4 native launches)"}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="gps_pretrain", choices=["gps_pretrain", "pointops_sa1", "pointops_sweep"])
+    ap.add_argument("--workload", default="gps_pretrain",
+                    choices=["gps_pretrain", "scanrefer", "objcls", "pointops_sa1", "pointops_sweep"])
+    ap.add_argument("--no-overlap", action="store_true", help="N > 1: one un-overlapped all-reduce between two graphs")
+    ap.add_argument("--no-equal-work", action="store_true", help="N = 1: skip the extra run with distributed autograd semantics")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying the captured CUDA graph")
     ap.add_argument("--no-kernel-rooflines", action="store_true")
@@ -251,16 +329,23 @@ def main():
             m, r = N // 32, 0.2 * (1024.0 / N) ** (1.0 / 3.0)
             idx = _ext.furthest_point_sampling(x, m)
             cen = torch.gather(x, 1, idx.long()[..., None].expand(-1, -1, 3)).contiguous()
-            _ext.ball_query(cen, x, r, 32)
+            for _ in range(max(1, min(warmup, 3)) - 1):          # warm-up (the first call above was one)
+                _ext.furthest_point_sampling(x, m)
+                _ext.ball_query(cen, x, r, 32)
             torch.cuda.synchronize()
-            e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-            e[0].record(stream)
-            idx = _ext.furthest_point_sampling(x, m)
-            e[1].record(stream)
-            _ext.ball_query(cen, x, r, 32)
-            e[2].record(stream)
-            torch.cuda.synchronize()
-            t = torch.tensor([e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2])], device=device, dtype=torch.float64)
+            iters = max(1, min(args.steps, 5))
+            tf_ = tb_ = 0.0
+            for _ in range(iters):
+                e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+                e[0].record(stream)
+                idx = _ext.furthest_point_sampling(x, m)
+                e[1].record(stream)
+                _ext.ball_query(cen, x, r, 32)
+                e[2].record(stream)
+                torch.cuda.synchronize()
+                tf_ += e[0].elapsed_time(e[1]) / iters
+                tb_ += e[1].elapsed_time(e[2]) / iters
+            t = torch.tensor([tf_, tb_], device=device, dtype=torch.float64)
             if world > 1:
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             tf_, tb_ = float(t[0]), float(t[1])
@@ -273,7 +358,8 @@ def main():
         if rank == 0:
             best = max(rows, key=lambda r_: r_["mpts_per_s"])
             print(json.dumps({"metric": "FPS+ball_query Mpts/s (sweep 16K-1M points)", "value": best["mpts_per_s"], "unit": "Mpts/s",
-                              "n_gpus": world, "steps": 1, "warmup": 1, "ms_per_step": best["fps_ms"] + best["ball_query_ms"],
+                              "n_gpus": world, "steps": max(1, min(args.steps, 5)), "warmup": max(1, min(warmup, 3)),
+                              "ms_per_step": best["fps_ms"] + best["ball_query_ms"],
                               "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                               "data": "synthetic", "config": {"workload": "pointops_sweep", "parallelism": f"dp{world}"},
                               "sweep": rows, "roofline": {"bound": "hbm", "peak": hbm, "unit": "GB/s", "peak_source": src,
@@ -292,17 +378,41 @@ def main():
         return 0
 
     NBUF = 3
-    np_batches = make_scene_batches(NBUF, SCENES, 42 + rank)
+    tf = weights.synthetic_tensor("text_features", (607, 768))
+    if args.workload == "objcls":
+        # BASELINE.json configs[1]: 64 objects x 1024 points per step (one "scene" of 64 valid objects), labels for the CE
+        from sceneverse_b200 import synthetic
+        OBJ = 64
+        np_batches = []
+        for i in range(NBUF):
+            d = synthetic.scene_batch(42 + rank + 1000 * i, B=1, O=OBJ, P=PTS, all_valid=True)
+            np_batches.append({k: d[k] for k in ("obj_fts", "obj_labels", "obj_masks")})
+        config.update(workload="objcls", objects_per_step=OBJ, scenes_per_gpu=None, objects_per_scene=None, global_batch=OBJ * max(world, 1),
+                      txt_len=None, scene_txt_len=None, losses=["obj_cls_loss (label smoothing 0.3)"], optimizer="AdamW",
+                      backbone="PointNet++ trainable, train-mode BatchNorm (model/objcls.py)",
+                      l2="3 distinct input batches rotated (working set of one step: ~1 GB of grouped activations > L2)")
+        ps = train.ObjClsStep(device, tf.to(device), dtype=torch.bfloat16, seed=1234, cuda_graph=not args.no_graph, num_gpu=1)
+        units_per_step, unit = OBJ, "objects/s"
+        metric = "ObjCls pre-train objects/sec (PointNet++ trainable)"
+    else:
+        np_batches = make_scene_batches(NBUF, SCENES, 42 + rank)
+        if args.workload == "scanrefer":
+            mcfg = M.scanrefer_config(world, text_features=tf)
+            for b_ in np_batches:
+                b_.pop("scene_txt_ids", None), b_.pop("scene_txt_masks", None)
+            config.update(workload="scanrefer", scene_txt_len=None, losses=["og3d_loss"],
+                          heads="GroundHeadV1 hidden 384 (configs/final/finetune/scanrefer_finetune.yaml)")
+            metric = "ScanRefer grounding fine-tune scenes/sec"
+        else:
+            mcfg = M.pretrain_config(world, text_features=tf)
+            metric = METRIC
+        ps = train.PretrainStep(mcfg, device, dtype=torch.bfloat16, seed=1234, cuda_graph=not args.no_graph,
+                                overlap_allreduce=not args.no_overlap)
+        units_per_step, unit = SCENES, "scenes/s"
     pinned = [{k: torch.from_numpy(v).pin_memory() for k, v in b.items()} for b in np_batches]
     resident = [{k: v.to(device) for k, v in p.items()} for p in pinned]
     h2d_bytes = sum(v.numel() * v.element_size() for v in pinned[0].values())
-    tf = weights.synthetic_tensor("text_features", (607, 768))
-    ps = train.PretrainStep(M.pretrain_config(world, text_features=tf), device, dtype=torch.bfloat16, seed=1234,
-                            cuda_graph=not args.no_graph)
     config["cuda_graph"] = bool(ps.graph_mode)
-    if world > 1:
-        config["dp_impl"] = ("graph(fwd+bwd) + one flat NCCL all-reduce + graph(clip+AdamW)" if ps.dp_graph
-                             else "torch DDP (bucketed NCCL all-reduce overlapped with backward)")
     host_loss = torch.zeros((), dtype=torch.float32).pin_memory()
 
     def step_resident(i):
@@ -354,8 +464,8 @@ def main():
         if world > 1:
             dist.barrier()
         launches = _lib.launch_count() - l0
-        if ps.graph_mode:   # replayed kernel nodes do not pass through the C-ABI launch counter: count them per replay
-            launches = steps * ps.native_launches_per_step
+        if ps.graph_mode and hasattr(ps, "native_launches_per_step"):
+            launches = steps * ps.native_launches_per_step   # replayed kernel nodes bypass the C-ABI launch counter
         t = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -366,37 +476,73 @@ def main():
         e2e_ms, _, _ = timed(step_e2e, args.steps, warmup)
     clocks = cs.summary()
     ms_per_step = total_ms / args.steps
-    value = world * SCENES / (ms_per_step * 1e-3)
-    e2e_value = world * SCENES / (e2e_ms / args.steps * 1e-3)
-    rt = rp = None
+    value = world * units_per_step / (ms_per_step * 1e-3)
+    e2e_value = world * units_per_step / (e2e_ms / args.steps * 1e-3)
+    phases = equal_work = None
+    if world > 1 and getattr(ps, "dp_graph", False) and ps.graph_opt is not None:
+        # where the data-parallel step goes when nothing is overlapped: graph(forward+backward) | NCCL all-reduce | graph(clip+AdamW)
+        pt = torch.tensor(ps.phase_times(dict(resident[0]), steps=5), device=device, dtype=torch.float64)
+        dist.all_reduce(pt, op=dist.ReduceOp.MAX)
+        phases = {"ms_fwd_bwd": float(pt[0]), "ms_allreduce": float(pt[1]), "ms_opt": float(pt[2]),
+                  "note": "un-overlapped path, 5 extra steps after the timed region, max over ranks"}
+    if world == 1 and args.workload == "gps_pretrain" and not args.no_equal_work and not args.no_graph:
+        # the step ONE rank of a data-parallel job executes (distributed autograd semantics of common/dist_utils.py:131-149: the
+        # between-batch negatives carry no gradient, so the scene-caption text-encoder backward disappears) — the equal-work
+        # N = 1 baseline of the scaling curve
+        ps.close()
+        mcfg2 = M.pretrain_config(1, text_features=tf)
+        mcfg2["emulate_dist"] = True
+        ps2 = train.PretrainStep(mcfg2, device, dtype=torch.bfloat16, seed=1234, cuda_graph=True)
+        t2, _, _ = (lambda f: timed(f, args.steps, warmup))(lambda i: ps2.step(dict(resident[i % NBUF])))
+        equal_work = {"ms_per_step": t2 / args.steps, "value": units_per_step / (t2 / args.steps * 1e-3), "unit": unit,
+                      "what": "N = 1 with the autograd semantics of the N > 1 step (detached between-batch negatives)"}
+        ps2.close()
+    rt = rp = ra = None
     if rank == 0 and not args.no_kernel_rooflines:
         rt, rp = kernel_rooflines(torch, device)
+        ra = attention_rooflines(torch, device)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if rank != 0:
         return 0
     from sceneverse_b200 import ops
-    out = {"metric": METRIC, "value": value, "unit": "scenes/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
+    launch_kind = ("one CUDA graph per step: forward + backward + all-reduce(behind the text encoder, overlapped) + all-reduce(text "
+                   "encoder) + clip/AdamW" if getattr(ps, "overlapped", False) else
+                   "CUDA graphs (forward+backward | NCCL all-reduce | clip+AdamW)" if getattr(ps, "dp_graph", False) else
+                   "whole step captured in one CUDA graph" if ps.graph_mode else "eager")
+    out = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": warmup,
            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
            "data": "synthetic", "config": config, "final_loss": loss,
-           "e2e": {"value": e2e_value, "unit": "scenes/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
+           "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
            "gpu_launches": int(launches), "clocks": clocks,
            "native_kernels_in_step": ["sa_sample_kernel (FPS + ball query, 2 SA levels)", "sa_mlp_kernel<SA1>", "sa_mlp_kernel<SA2>",
-                                      "gemm_kernel (SA3 chain + fc with fused shift/ReLU/row-max; LM-head decoder with fused bias)",
+                                      "gemm_kernel<BN, FWD|DGRAD|WGRAD, 1|2 CTAs>: every nn.Linear of the step in all three directions "
+                                      "(bias / ReLU / GELU / dropout / activation-derivative epilogues, split-K wgrad + bias gradient "
+                                      "accumulated into the flat gradient buffer), SA3 chain + fc, LM-head decoder",
                                       "pairwise_locs_kernel",
-                                      "attn_fwd_kernel / attn_bwd_kernel x16 (spatial gate x4, joint MHA x4, BERT self-attention x8; "
-                                      "in-kernel attention dropout)",
+                                      "attn_fwd_kernel / attn_bwd_kernel x16 (spatial gate x4, joint MHA x4, BERT self-attention x8; packed "
+                                      "QKV, in-kernel attention dropout)",
                                       "ln_fwd / ln_bwd_dx / ln_bwd_dgb kernels x44 (dropout + residual + LayerNorm)",
-                                      "ce_fwd_bwd_kernel (masked-LM CE on the padded vocabulary)",
+                                      "ce_fwd_bwd_kernel + scale_inplace_kernel (masked-LM CE on the padded vocabulary)",
+                                      "embedding_bwd_kernel / colsum kernels (BERT embedding gradients)",
+                                      "sqnorm_partial_kernel + adamw_flat_kernel (clip + AdamW + bf16 shadows over the flat buffers)",
                                       "norm_allgather_kernel (N > 1: contrastive exchange over NVLink peer memory)"],
-           "library_ops_in_step": ["plain linears forward/backward (cuBLAS)", "FFN dropout / GELU / embedding (ATen)",
-                                   "AdamW + gradient clipping (torch fused / foreach)", "gradient all-reduce (NCCL via DDP, N > 1)"],
-           "launch": ("CUDA graphs (forward+backward | NCCL all-reduce | clip+AdamW)" if ps.dp_graph else
-                      "whole step captured in one CUDA graph" if ps.graph_mode else "eager")}
+           "library_ops_in_step": ["residual / positional adds, dtype casts, softmax of the 64x64 contrastive logits, masked fills (ATen "
+                                   "elementwise, ~14 % of the step)", "two 64x768x64 InfoNCE logit matmuls + the 607-class object head (cuBLAS, "
+                                   "0.5 %)", "gradient all-reduce (NCCL, N > 1)"],
+           "launch": launch_kind}
+    if phases is not None:
+        out["phases_unoverlapped"] = phases
+    if equal_work is not None:
+        out["equal_work_n1"] = equal_work
+    if world > 1:
+        out["allreduce_overlapped"] = bool(getattr(ps, "overlapped", False))
     if rt is not None:
         out["roofline"], out["roofline_pointops"] = rt, rp
-    if not args.no_cpu_baseline:
+    if ra is not None:
+        out["roofline_attention"] = ra
+    if not args.no_cpu_baseline and args.workload == "gps_pretrain":
         scenes = 2
         step = cpu_reference_step_fn(scenes)
         step()
@@ -404,8 +550,9 @@ def main():
         step()
         dt = time.perf_counter() - t0
         out["cpu_baseline"] = {"value": scenes / dt, "unit": "scenes/s", "cores": cpu_threads(), "kind": "port",
-                               "sample": f"1 step of {scenes} scenes (of {SCENES}) x {OBJS} x {PTS}, fp32, same modules on CPU "
-                                         "with oracle/pointops_ref.c as `_ext`"}
+                               "sample": f"1 step of {scenes} scenes (of the {SCENES} of a GPU step: scenes/s EXTRAPOLATED from "
+                                         f"{scenes}/{SCENES} of the batch) x {OBJS} x {PTS}, fp32, same modules on CPU with "
+                                         "oracle/pointops_ref.c as `_ext`"}
     print(json.dumps(out))
     return 0
 

@@ -118,6 +118,9 @@ class OpenVocab(nn.Module):
         if 'cur_step' not in data_dict:
             data_dict['cur_step'], data_dict['total_steps'] = 1, 1
         lang = self.lang_encoder(data_dict['txt_ids'], data_dict['txt_masks'])
+        hook = getattr(self, "_lang_grad_hook", None)
+        if hook is not None and lang.requires_grad:
+            lang.register_hook(hook)       # train.PretrainStep: launch point of the early gradient all-reduce
         if self.use_scene_cap:
             data_dict['scene_text_embed'] = self.lang_encoder(data_dict['scene_txt_ids'], data_dict['scene_txt_masks'])[:, 0]
         obj, obj_pre, obj_cls_raw = self.point_encoder(data_dict['obj_fts'].float(), data_dict['obj_locs'],

@@ -68,6 +68,10 @@ class _SymmetricInfoNCE(nn.Module):
     def __init__(self, cfg):
         super().__init__()
         self.distributed = _num_gpu(cfg) > 1
+        # single-process run with the DISTRIBUTED autograd semantics (the gathered negatives of common/dist_utils.py:131-149
+        # carry no gradient): what one rank of a data-parallel job computes, minus the exchange — the equal-work baseline
+        # of the scaling curve (bench.py)
+        self.emulate_dist = bool(cfg.get("emulate_dist", False)) if isinstance(cfg, dict) else bool(getattr(cfg, "emulate_dist", False))
         self.logit_scale = nn.Parameter((torch.ones([]) * np.log(1 / 0.07)).exp())
 
     def info_nce(self, a_feats, text_feats):
@@ -85,6 +89,8 @@ class _SymmetricInfoNCE(nn.Module):
             text_feats = F.normalize(text_feats, dim=-1, p=2)
             if self.distributed:
                 a_feats, text_feats = all_gather([a_feats, text_feats])
+            elif self.emulate_dist:
+                a_feats, text_feats = a_feats.detach(), text_feats.detach()
         labels = torch.arange(text_feats.shape[0], device=text_feats.device)
         t2a = logit_scale * text_feats @ a_feats.t()
         a2t = logit_scale * a_feats @ text_feats.t()
@@ -109,7 +115,7 @@ class TextSceneBetweenBatch(_SymmetricInfoNCE):
 class Loss(nn.Module):
     """optim/loss/loss.py:111-148 list-loss container (cfg.model.loss_list / vis_loss_list)."""
 
-    def __init__(self, loss_list, vis_loss_list=None, num_gpu=1):
+    def __init__(self, loss_list, vis_loss_list=None, num_gpu=1, emulate_dist=False):
         super().__init__()
         self.selected_keys = list(loss_list)
         self.all_keys = list(dict.fromkeys(list(vis_loss_list or []) + self.selected_keys))
@@ -118,7 +124,7 @@ class Loss(nn.Module):
             if k in globals() and callable(globals()[k]) and not isinstance(globals()[k], type):
                 self.loss_fn[k] = globals()[k]
             else:
-                self.loss_fn[k] = LOSS_REGISTRY.get(k)({"num_gpu": num_gpu})
+                self.loss_fn[k] = LOSS_REGISTRY.get(k)({"num_gpu": num_gpu, "emulate_dist": emulate_dist})
                 setattr(self, k, self.loss_fn[k])
 
     def forward(self, data_dict):

@@ -25,7 +25,8 @@ class StepModule(nn.Module):
         super().__init__()
         self.model = M.OpenVocab(cfg)
         c = M.to_cfg(cfg)
-        self.loss = L.Loss(c.model.loss_list, c.model.vis_loss_list, num_gpu=c.num_gpu)
+        self.loss = L.Loss(c.model.loss_list, c.model.vis_loss_list, num_gpu=c.num_gpu,
+                           emulate_dist=bool(c.get("emulate_dist", False)))
         for n, p in self.model.named_parameters():
             if n.startswith(STATIC_UNUSED):
                 p.requires_grad = False
@@ -37,7 +38,8 @@ class StepModule(nn.Module):
 
 
 class PretrainStep:
-    def __init__(self, cfg, device, total_steps=100000, dtype=torch.bfloat16, ddp=None, seed=0, cuda_graph=False):
+    def __init__(self, cfg, device, total_steps=100000, dtype=torch.bfloat16, ddp=None, seed=0, cuda_graph=False,
+                 overlap_allreduce=True):
         """cuda_graph=True (single process, CUDA): after a few eager steps the whole step — forward, losses, backward,
         gradient clipping and AdamW — is captured once into a CUDA graph and replayed from static input buffers; the host
         then issues one graph launch per step instead of ~2000 kernel launches.  Dropout stays random: torch's own dropout
@@ -59,6 +61,12 @@ class PretrainStep:
         # the contrastive exchange inside graph A is the native peer-memory kernel with a device-resident epoch.
         self.graph_mode = bool(cuda_graph) and self.device.type == "cuda"
         self.dp_graph = self.graph_mode and self.use_ddp
+        # several ranks: the gradient all-reduce of everything BEHIND the text encoder (spatial layers, joint layers, heads,
+        # ~57 % of the 491 MB) is launched from an autograd hook as soon as those gradients are final and runs on NCCL's
+        # stream under the text encoder's backward; both collectives are captured in the step's CUDA graph
+        self.overlap_allreduce = bool(overlap_allreduce)
+        self.overlapped = False
+        self._ar_work = None
         if self.dp_graph:
             self.use_ddp = False
         warm = self.cfg.solver.sched.args.warmup_steps * self.cfg.num_gpu
@@ -138,13 +146,36 @@ class PretrainStep:
             ops.refresh_shadows()
         # gradients live in the flat buffer: the wgrad kernels accumulate into it directly (no AccumulateGrad adds)
         prev, ops.DIRECT_GRAD[0] = ops.DIRECT_GRAD[0], self.flat_grads is not None
+        self._ar_work = None
+        self.module.model._lang_grad_hook = self._early_allreduce if self._overlap_now else None
         try:
             with torch.autocast(self.device.type, dtype=self.dtype, enabled=self.dtype != torch.float32):
                 total, _ = self.module(dict(self.static_batch))
             total.backward()
         finally:
             ops.DIRECT_GRAD[0] = prev
+            self.module.model._lang_grad_hook = None
         return total.detach()
+
+    _overlap_now = False
+
+    def _early_allreduce(self, grad):
+        """autograd hook on the text encoder's output: its gradient is complete, so (the autograd engine runs nodes in reverse
+        forward order) every node created after the text encoder's forward has run its backward — the gradients of the
+        spatial layers, joint layers, heads and losses are final.  Their slice of the flat buffer goes out now."""
+        if self._ar_work is None:
+            tail = self.flat_grads.flat[self._lang_end:]
+            self._ar_work = dist.all_reduce(tail, op=dist.ReduceOp.AVG, async_op=True)
+        return None
+
+    def _finish_allreduce(self):
+        head = self.flat_grads.flat[:self._lang_end]
+        if self._ar_work is not None:
+            self._ar_work.wait()
+            dist.all_reduce(head, op=dist.ReduceOp.AVG)
+        else:                                   # the hook did not fire (no gradient reached the text encoder's output)
+            self.flat_grads.all_reduce_mean()
+        self._ar_work = None
 
     def _raw_opt(self):
         if isinstance(self.flat_grads, FlatState):
@@ -160,9 +191,23 @@ class PretrainStep:
     def _raw_step(self):
         loss = self._raw_fwd_bwd()
         if self.flat_grads is not None:
-            self.flat_grads.all_reduce_mean()
+            if self._overlap_now:
+                self._finish_allreduce()
+            else:
+                self.flat_grads.all_reduce_mean()
         self._raw_opt()
         return loss
+
+    def _lang_boundary(self):
+        """Offset in the flat buffers where the text encoder's parameters end — valid only if they form the head of the layout
+        (they do: model.get_opt_params lists the language encoder first)."""
+        flat = self.flat_grads
+        lang = {id(p) for p in self.module.model.lang_encoder.parameters()}
+        end_lang = max((flat.offsets[i] + p.numel() for p in flat.params for i in [id(p)] if i in lang), default=0)
+        first_other = min((flat.offsets[id(p)] for p in flat.params if id(p) not in lang), default=flat.n)
+        if end_lang == 0 or end_lang > first_other:
+            return None
+        return (end_lang + 7) // 8 * 8 if (end_lang + 7) // 8 * 8 <= first_other else end_lang
 
     def _advance_lr(self):
         self._sched_step += 1
@@ -207,6 +252,30 @@ class PretrainStep:
             with torch.cuda.graph(self.graph_opt, pool=self.graph.pool()):
                 self._raw_opt()
         self.native_launches_per_step = _lib.launch_count() - n0   # native kernel nodes replayed per step
+        if self.dp_graph and self.overlap_allreduce:
+            self._lang_end = self._lang_boundary()
+            if self._lang_end is not None:
+                try:
+                    self._overlap_now = True
+                    side.wait_stream(cur)
+                    with torch.cuda.stream(side):       # one eager step through the hook path (NCCL warm-up on its stream)
+                        self._raw_step()
+                        self._advance_lr()
+                    cur.wait_stream(side)
+                    torch.cuda.synchronize(self.device)
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, pool=self.graph.pool()):
+                        loss = self._raw_step()       # forward + backward + both all-reduces + clip/AdamW: ONE graph
+                    self.graph_overlap, self.static_loss_overlap = g, loss
+                    self.overlapped = True
+                except Exception as e:                  # NCCL capture unsupported here: keep the two-graph path
+                    self._overlap_now = False
+                    torch.cuda.synchronize(self.device)
+                    if dist.get_rank() == 0:
+                        print(f"[sceneverse_b200] overlapped all-reduce unavailable ({type(e).__name__}: {e}); "
+                              "using graph | all-reduce | graph")
+                finally:
+                    self._overlap_now = False
 
     def _dp_graph_possible(self):
         """Graph A must not contain an NCCL collective: with several ranks the contrastive exchange has to be the native
@@ -230,12 +299,36 @@ class PretrainStep:
             src = data_dict[k]
             if src.data_ptr() != dst.data_ptr():
                 dst.copy_(src, non_blocking=True)
+        if self.overlapped:
+            self.graph_overlap.replay()
+            self._advance_lr()
+            return self.static_loss_overlap
         self.graph.replay()
         if self.dp_graph:
             self.flat_grads.all_reduce_mean()
             self.graph_opt.replay()
         self._advance_lr()
         return self.static_loss
+
+    def phase_times(self, data_dict, steps=5):
+        """(ms_fwd_bwd, ms_allreduce, ms_opt) of the NON-overlapped data-parallel step (graph | NCCL | graph), CUDA events on
+        the current stream; the parameters do advance (these are real steps)."""
+        assert self.dp_graph and self.graph is not None and self.graph_opt is not None
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(steps)]
+        for k, dst in self.static_batch.items():
+            if data_dict[k].data_ptr() != dst.data_ptr():
+                dst.copy_(data_dict[k], non_blocking=True)
+        for e in ev:
+            e[0].record()
+            self.graph.replay()
+            e[1].record()
+            self.flat_grads.all_reduce_mean()
+            e[2].record()
+            self.graph_opt.replay()
+            e[3].record()
+            self._advance_lr()
+        torch.cuda.synchronize(self.device)
+        return tuple(sum(e[i].elapsed_time(e[i + 1]) for e in ev) / steps for i in range(3))
 
     def step(self, data_dict):
         """data_dict: tensors already on self.device. Returns the (detached) total loss tensor — no host sync."""
@@ -406,3 +499,51 @@ def batch_to_device(np_batch, device, pinned=None, non_blocking=True):
         src = pinned[k] if pinned is not None else torch.from_numpy(v)
         out[k] = src.to(device, non_blocking=non_blocking)
     return out
+
+
+class ObjClsStep:
+    """Object-level pre-training step (reference: model/objcls.py:64-98 + optim/loss/loss.py:96-102, BASELINE.json configs[1]):
+    PointNet++ TRAINABLE with train-mode BatchNorm -> dropout -> 607-way open-vocabulary logits -> label-smoothed CE ->
+    AdamW.  The point operators and their gradients (group_points_grad / gather) are the native kernels; conv / BatchNorm
+    statistics run on cuDNN / ATen (the fused tensor-core SA-MLP is the eval-BN form).  cuda_graph=True captures the whole
+    step after three eager ones."""
+
+    def __init__(self, device, text_embeds, lr=1e-3, dtype=torch.bfloat16, seed=0, cuda_graph=False, num_gpu=1):
+        torch.manual_seed(seed)
+        self.device, self.dtype = torch.device(device), dtype
+        self.model = M.ObjCls({"num_gpu": num_gpu, "solver": {"lr": lr}}, text_embeds=text_embeds).to(self.device).train()
+        self.graph_mode = bool(cuda_graph) and self.device.type == "cuda"
+        self.optimizer = torch.optim.AdamW(self.model.parameters(), lr=torch.tensor(lr, device=self.device) if self.graph_mode else lr,
+                                           fused=self.device.type == "cuda", capturable=self.graph_mode)
+        self.graph = self.static_batch = self.static_loss = None
+
+    def _raw(self, batch):
+        self.optimizer.zero_grad(set_to_none=False)
+        with torch.autocast(self.device.type, dtype=self.dtype, enabled=self.dtype != torch.float32):
+            out = self.model(dict(batch))
+            loss = L.obj_cls_loss(out)
+        loss.backward()
+        self.optimizer.step()
+        return loss.detach()
+
+    def step(self, batch):
+        if not self.graph_mode:
+            return self._raw(batch)
+        if self.graph is None:
+            self.static_batch = {k: v.clone() for k, v in batch.items() if torch.is_tensor(v)}
+            cur = torch.cuda.current_stream(self.device)
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    self._raw(self.static_batch)
+            cur.wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.static_loss = self._raw(self.static_batch)
+        for k, dst in self.static_batch.items():
+            if batch[k].data_ptr() != dst.data_ptr():
+                dst.copy_(batch[k], non_blocking=True)
+        self.graph.replay()
+        return self.static_loss

@@ -64,3 +64,15 @@ def test_fused_normalize_allgather_two_ranks():
                           os.path.join(ROOT, "scripts", "fused_allgather_2rank.py")], capture_output=True, text=True,
                          timeout=600, cwd=ROOT)
     assert "FUSED_ALLGATHER_OK=True" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_overlapped_gradient_allreduce_two_ranks():
+    """train.PretrainStep at 2 ranks: all-reduce split at the text encoder boundary, launched from an autograd hook and
+    captured in the step graph, vs the un-overlapped step (needs 2 GPUs)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29578",
+                          os.path.join(ROOT, "scripts", "dp_overlap_2rank.py")], capture_output=True, text=True,
+                         timeout=900, cwd=ROOT)
+    assert "DP_OVERLAP_OK=True" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
