@@ -539,9 +539,12 @@ class ObjClsStep:
                     self._raw(self.static_batch)
             cur.wait_stream(side)
             torch.cuda.synchronize(self.device)
+            from . import _lib
+            n0 = _lib.launch_count()
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
                 self.static_loss = self._raw(self.static_batch)
+            self.native_launches_per_step = _lib.launch_count() - n0
         for k, dst in self.static_batch.items():
             if batch[k].data_ptr() != dst.data_ptr():
                 dst.copy_(batch[k], non_blocking=True)
