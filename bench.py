@@ -283,7 +283,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="gps_pretrain",
                     choices=["gps_pretrain", "scanrefer", "objcls", "pointops_sa1", "pointops_sweep"])
-    ap.add_argument("--no-overlap", action="store_true", help="N > 1: one un-overlapped all-reduce between two graphs")
+    ap.add_argument("--overlap", action="store_true", help="N > 1: split the gradient all-reduce and capture it in the step graph (experimental)")
     ap.add_argument("--no-equal-work", action="store_true", help="N = 1: skip the extra run with distributed autograd semantics")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying the captured CUDA graph")
@@ -407,7 +407,7 @@ def main():
             mcfg = M.pretrain_config(world, text_features=tf)
             metric = METRIC
         ps = train.PretrainStep(mcfg, device, dtype=torch.bfloat16, seed=1234, cuda_graph=not args.no_graph,
-                                overlap_allreduce=not args.no_overlap)
+                                overlap_allreduce=args.overlap)
         units_per_step, unit = SCENES, "scenes/s"
     pinned = [{k: torch.from_numpy(v).pin_memory() for k, v in b.items()} for b in np_batches]
     resident = [{k: v.to(device) for k, v in p.items()} for p in pinned]

@@ -482,17 +482,21 @@ def calc_pairwise_locs(obj_centers, obj_whls, eps=1e-10, pairwise_rel_type='cent
 
 def attention(q, k, v, num_heads, key_padding_mask=None, dropout_p=0.0):
     """Scaled-dot-product attention on packed heads: q (B,Lq,E), k/v (B,Lk,E) -> (B,Lq,E).
-    key_padding_mask (B,Lk) bool, True = ignore (nn.MultiheadAttention convention)."""
+    key_padding_mask (B,Lk) bool, True = ignore (nn.MultiheadAttention convention).
+    bf16 CUDA tensors run on the native tcgen05 kernels (head dim 64, <= 384 tokens — every shape of the GPS stack) and an
+    unsupported bf16 shape RAISES: there is no silent library fallback on the product path.  fp32 tensors (CPU host-logic
+    tests, the fp32 parity path on the GPU) use the torch formulation."""
     B, Lq, E = q.shape
     Lk, hd = k.shape[1], E // num_heads
-    if hd == 64 and Lk <= 384 and _native_ok(q, k, v):
+    if _native_ok(q, k, v):
+        if hd != 64 or Lk > 384 or Lq > 384:
+            raise NotImplementedError(f"native attention supports head dim 64 and <= 384 tokens (got head dim {hd}, Lq {Lq}, Lk {Lk})")
         needs_grad = torch.is_grad_enabled() and (q.requires_grad or k.requires_grad or v.requires_grad)
         if not needs_grad and dropout_p == 0.0:
             from . import native
             return native.attention(q, k, v, num_heads, key_padding_mask=key_padding_mask)
-        if Lq <= 384:
-            return _AttentionFn.apply(q, k, v, None, None, key_padding_mask, num_heads, 0, float(dropout_p),
-                                      _next_dropout_seed() if dropout_p > 0.0 else 0)
+        return _AttentionFn.apply(q, k, v, None, None, key_padding_mask, num_heads, 0, float(dropout_p),
+                                  _next_dropout_seed() if dropout_p > 0.0 else 0)
     qh = q.view(B, Lq, num_heads, hd).transpose(1, 2)
     kh = k.view(B, Lk, num_heads, hd).transpose(1, 2)
     vh = v.view(B, Lk, num_heads, hd).transpose(1, 2)
@@ -504,10 +508,14 @@ def attention(q, k, v, num_heads, key_padding_mask=None, dropout_p=0.0):
 
 
 def spatial_attention(q, k, v, spatial_weights, pairwise_locs, n_head, spatial_n_head, key_padding_mask=None):
-    """Dispatch: bf16 CUDA tensors with head dim 64 -> fused tcgen05 kernel (attention map not returned: every reference
-    caller discards it); anything else -> the torch formulation below."""
-    if _native_ok(q, k, v) and q.shape[-1] // n_head == 64 and k.shape[1] <= 384:
-        fn = _AttentionFn if (spatial_n_head == n_head and q.shape[1] <= 384) else _SpatialAttentionRecomputeFn
+    """bf16 CUDA tensors -> fused tcgen05 kernels, forward and backward (attention map not returned: every reference caller
+    discards it); the GPS configurations use one gate per head (spatial_multihead=True), a gate shared across heads keeps the
+    native forward with a recomputed backward.  An unsupported bf16 shape raises.  fp32 tensors -> the torch formulation
+    below (CPU host-logic tests, fp32 parity path)."""
+    if _native_ok(q, k, v):
+        if q.shape[-1] // n_head != 64 or k.shape[1] > 384 or q.shape[1] > 384:
+            raise NotImplementedError("native spatial attention supports head dim 64 and <= 384 objects")
+        fn = _AttentionFn if spatial_n_head == n_head else _SpatialAttentionRecomputeFn
         out = fn.apply(q, k, v, spatial_weights.float(), pairwise_locs.float(), key_padding_mask, n_head, spatial_n_head)
         return out, None
     return _spatial_attention_torch(q, k, v, spatial_weights, pairwise_locs, n_head, spatial_n_head, key_padding_mask)

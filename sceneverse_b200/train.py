@@ -39,7 +39,7 @@ class StepModule(nn.Module):
 
 class PretrainStep:
     def __init__(self, cfg, device, total_steps=100000, dtype=torch.bfloat16, ddp=None, seed=0, cuda_graph=False,
-                 overlap_allreduce=True):
+                 overlap_allreduce=False):
         """cuda_graph=True (single process, CUDA): after a few eager steps the whole step — forward, losses, backward,
         gradient clipping and AdamW — is captured once into a CUDA graph and replayed from static input buffers; the host
         then issues one graph launch per step instead of ~2000 kernel launches.  Dropout stays random: torch's own dropout
@@ -61,9 +61,11 @@ class PretrainStep:
         # the contrastive exchange inside graph A is the native peer-memory kernel with a device-resident epoch.
         self.graph_mode = bool(cuda_graph) and self.device.type == "cuda"
         self.dp_graph = self.graph_mode and self.use_ddp
-        # several ranks: the gradient all-reduce of everything BEHIND the text encoder (spatial layers, joint layers, heads,
-        # ~57 % of the 491 MB) is launched from an autograd hook as soon as those gradients are final and runs on NCCL's
-        # stream under the text encoder's backward; both collectives are captured in the step's CUDA graph
+        # several ranks, opt-in: the gradient all-reduce of everything BEHIND the text encoder (spatial layers, joint layers,
+        # heads, ~57 % of the 491 MB) is launched from an autograd hook as soon as those gradients are final and runs on NCCL's
+        # stream under the text encoder's backward; both collectives are captured in the step's CUDA graph.  Parity with the
+        # plain path is checked at 2 ranks (scripts/dp_overlap_2rank.py); the long-running bench hung with it on the 2-GPU box
+        # (round 2), so the default is the un-overlapped graph | all-reduce | graph path.
         self.overlap_allreduce = bool(overlap_allreduce)
         self.overlapped = False
         self._ar_work = None

@@ -22,7 +22,9 @@ def run(overlap):
             m.p = 0.0
         if hasattr(m, "dropout") and isinstance(m.dropout, float):
             m.dropout = 0.0
-    losses = [float(ps.step(dict(batch))) for _ in range(3)]
+    # the overlapped capture runs one more eager warm-up step than the plain one: align the two runs on the optimisation step
+    losses = [float(ps.step(dict(batch))) for _ in range(3 if overlap else 4)]
+    losses = losses[-3:]
     params = {n: p.detach().float().clone() for n, p in ps.module.named_parameters() if p.requires_grad}
     info = (ps.overlapped, ps.dp_graph)
     ps.close(); ops.clear_shadows()

@@ -332,3 +332,45 @@ def test_linear_fn_matches_autocast_linear():
     for g, w, name in zip(got, (yr.detach().float(), xr.grad, Wr.grad, br.grad), "yxWb"):
         err = (g - w).abs().max().item() / (w.abs().max().item() + 1e-9)
         assert err < 1e-2, (name, err)
+
+
+def test_rerouted_bert_matches_huggingface_bert_gpu():
+    """The text encoder (reference: modules/language/bert.py:8-26, HF BertModel with 4 layers) with its linears, self-attention,
+    feed-forward and LayerNorms re-routed onto the native kernels vs the UNPATCHED HuggingFace module with the same weights:
+    eval mode, bf16 autocast for the native path, fp32 for HF; also one training-mode backward to the embeddings."""
+    from transformers import BertConfig, BertModel
+    from sceneverse_b200 import model as M
+    from sceneverse_b200.modules.layers import route_linears
+    torch.manual_seed(0)
+    enc = route_linears(M.BERTLanguageEncoder(None)).cuda().eval()
+    ref = BertModel(BertConfig(hidden_size=768, num_hidden_layers=4, num_attention_heads=12, type_vocab_size=2)).cuda().eval()
+    ref.load_state_dict(enc.model.state_dict())
+    ids = torch.randint(1000, 30000, (8, 50), device="cuda")
+    mask = (torch.arange(50, device="cuda")[None, :] < torch.tensor([50, 12, 30, 50, 8, 44, 50, 25], device="cuda")[:, None]).long()
+    with torch.no_grad():
+        want = ref(ids, mask).last_hidden_state
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            got = enc(ids, mask)
+    valid = mask.bool()
+    err = (got.float() - want)[valid].abs().max().item() / want[valid].abs().max().item()
+    assert err < 3e-2, err
+    # training mode, dropout off: gradients reach every parameter the HF module trains (except the unused pooler)
+    enc.train()
+    for m in enc.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = enc(ids, mask)
+    (out.float() * valid[..., None]).sum().backward()
+    missing = [n for n, p in enc.named_parameters() if p.grad is None and "pooler" not in n]
+    assert not missing, missing
+    ref.train()
+    for m in ref.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    (ref(ids, mask).last_hidden_state * valid[..., None]).sum().backward()
+    for (n, p), (_, q) in zip(enc.model.named_parameters(), ref.named_parameters()):
+        if "pooler" in n:
+            continue
+        rel = (p.grad.float() - q.grad).abs().max().item() / (q.grad.abs().max().item() + 1e-6)
+        assert rel < 8e-2, (n, rel)
