@@ -93,6 +93,26 @@ int sv_sa_sample_f32(const float *xyz, int B, int N, int m, float radius, int ns
                      float *new_xyz, int *ball_idx, int m2, float radius_2, int nsample2, int *fps_idx2,
                      float *new_xyz2, int *ball_idx2, void *stream);
 
+/* ---- device-side input pipeline -----------------------------------------------------------------------
+ * Builds the model's per-object tensors from ragged raw scene data on the GPU: replaces the per-object numpy loop of
+ * data/datasets/base.py:697-741 (`_obj_processing_post`) and the padding of data/datasets/dataset_wrapper.py:62-72.
+ * raw_points (total,6) f32 [xyz rgb]; slot_offsets (n_slots+1) int64 CSR over the B*O object slots (empty range = padded
+ * slot).  Per slot: obj_locs (6) = [mean xyz, max-min] of the raw points; P points sampled uniformly (without replacement
+ * when the object has >= P points, with replacement otherwise), centred on the SAMPLE mean, divided by the sample's max norm
+ * (1 when < 1e-6), colours untouched; empty slots: all-ones points, zero locs, mask 0.  sample_idx (n_slots,P) i32 may be
+ * NULL (receives the chosen raw indices, -1 for empty slots).  Randomness = counter hash of (seed, slot, k). */
+int sv_scene_prep_f32(const float *raw_points, const long long *slot_offsets, int n_slots, int P, unsigned long long seed,
+                      float *obj_fts, float *obj_locs, unsigned char *obj_masks, int *sample_idx, void *stream);
+/* BERT masked-LM corruption (data/data_utils.py:76-104 `random_word`): for tokens with attention_mask != 0, with probability
+ * mask_ratio the label is the original id and the token becomes [MASK] (80 %), a uniform random id (10 %) or stays (10 %);
+ * every other label is -1.  ids / attention_mask / out_ids / labels: (n_tokens) int64. */
+int sv_token_mask(const long long *ids, const long long *attention_mask, long long n_tokens, float mask_ratio,
+                  long long mask_token_id, long long vocab_size, unsigned long long seed, long long *out_ids,
+                  long long *labels, void *stream);
+/* random_point_cloud (data/data_utils.py:107-121): out[i] = valid[i] && u_i >= drop_ratio (bytes). */
+int sv_coin_mask(const unsigned char *valid, long long n, float drop_ratio, unsigned long long seed, unsigned char *out,
+                 void *stream);
+
 #ifdef __cplusplus
 }
 #endif
