@@ -359,16 +359,18 @@ def test_rerouted_bert_matches_huggingface_bert_gpu():
     for m in enc.modules():
         if isinstance(m, torch.nn.Dropout):
             m.p = 0.0
+    # a random read-out: the plain sum of a LayerNorm output is constant, its gradient would be rounding noise
+    proj = torch.randn(50, 768, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
     with torch.autocast("cuda", dtype=torch.bfloat16):
         out = enc(ids, mask)
-    (out.float() * valid[..., None]).sum().backward()
+    (out.float() * proj * valid[..., None]).sum().backward()
     missing = [n for n, p in enc.named_parameters() if p.grad is None and "pooler" not in n]
     assert not missing, missing
     ref.train()
     for m in ref.modules():
         if isinstance(m, torch.nn.Dropout):
             m.p = 0.0
-    (ref(ids, mask).last_hidden_state * valid[..., None]).sum().backward()
+    (ref(ids, mask).last_hidden_state * proj * valid[..., None]).sum().backward()
     for (n, p), (_, q) in zip(enc.model.named_parameters(), ref.named_parameters()):
         if "pooler" in n:
             continue
