@@ -305,236 +305,6 @@ __global__ void __launch_bounds__(32) sa_sample_kernel(const SaSampleParams p) {
   }
 }
 
-// ---- two warps per cloud (513 <= N <= 1024: 32 register slots per lane in the one-warp kernel) --------------------------------
-// The one-warp kernel above is issue- and latency-bound at 12 resident warps per SM (168 registers, 21 KB of shared memory
-// per cloud): ncu showed 47 % issue utilisation and 0.67 eligible warps per cycle.  Here a cloud is shared by the TWO warps of
-// a 64-thread CTA: warp w owns slots [16 w, 16 w + 16) (half the registers, twice the warps per cloud), the per-iteration
-// arg-max is combined through shared memory with ONE CTA barrier (each warp publishes its (max key, winning lane rank,
-// candidate index); ties between the warps go to warp 0, whose slots precede warp 1's in the reference's order), the hit
-// words of four slots leave in one 128-bit store, and after the last iteration warp 1 compacts the level-1 ball query while
-// warp 0 runs the level-2 sampling.  Same arithmetic, same tie-breaks, bit-identical indices.
-struct Xchg {
-  unsigned key, rank;
-  int idx, pad;
-};
-
-__global__ void __launch_bounds__(64) sa_sample2w_kernel(const SaSampleParams p) {
-  extern __shared__ __align__(16) float sm[];
-  constexpr int H = 16, NP = 8;                   // slots / register pairs per lane
-  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const int b = blockIdx.x;
-  const int N = p.N, m = p.m, nsample = p.nsample;
-  const int n3 = 3 * N;
-  const int rs = nsample | 1;
-  float *pts = sm;                                                 // [3N] AoS copy of the cloud (later: compaction staging)
-  int *kbase = reinterpret_cast<int *>(sm + ((n3 + 3) & ~3));      // [32]
-  int *slot_of_chunk = kbase + 32;                                 // [32]
-  unsigned *W = reinterpret_cast<unsigned *>(slot_of_chunk + 32);  // [32][36] hit words: row = centre, col = slot (16-byte rows)
-  float *rec = reinterpret_cast<float *>(W + 32 * 36);             // [2][16]
-  Xchg *xc = reinterpret_cast<Xchg *>(rec + 32);                   // [2 parities][2 warps]
-
-  stage_floats(pts, p.xyz + (size_t)b * n3, n3, tid, 64);
-  if (tid < 32 && tid < p.spt) {
-    const int u = tid / p.Qmax, r = tid - u * p.Qmax;
-    const int kb = r * p.BS + (brevn(u, p.lgBS - 5) << 5);
-    kbase[tid] = kb;
-    slot_of_chunk[kb >> 5] = tid;
-  }
-  __syncthreads();
-
-  u64 px[NP], py[NP], pz[NP];
-  float pt[H];
-#pragma unroll
-  for (int q = 0; q < NP; ++q) {
-    float cx[2], cy[2], cz[2];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int i = 2 * q + h;               // local slot; global slot = w * H + i
-      float x = FAR_AWAY, y = FAR_AWAY, z = FAR_AWAY, t = -2.0f;
-      const int gi = w * H + i;
-      if (gi < p.spt) {
-        const int k = kbase[gi] + lane;
-        if (k < N) {
-          x = pts[3 * k + 0];
-          y = pts[3 * k + 1];
-          z = pts[3 * k + 2];
-          const float mag = __fmaf_rn(z, z, __fmaf_rn(x, x, __fmul_rn(y, y)));
-          if (!mag_skipped(mag)) t = 1e10f;
-        }
-      }
-      cx[h] = x; cy[h] = y; cz[h] = z;
-      pt[i] = t;
-    }
-    px[q] = pack2(cx[0], cx[1]);
-    py[q] = pack2(cy[0], cy[1]);
-    pz[q] = pack2(cz[0], cz[1]);
-  }
-
-  const float r2 = __fmul_rn(p.radius, p.radius);
-  const int nchunks = (N + 31) >> 5;
-  int old = 0;
-  float x1 = pts[0], y1 = pts[1], z1 = pts[2];
-  int my_idx = 0;
-  float mcx = 0.f, mcy = 0.f, mcz = 0.f;
-  const unsigned rk = (unsigned)brevn(lane, 5);
-  for (int j = 0; j < m; ++j) {
-    const int jr = j & 31;
-    const u64 X1 = pack2(x1, x1), Y1 = pack2(y1, y1), Z1 = pack2(z1, z1);
-    unsigned *wrow = W + jr * 36 + w * H;
-    unsigned hw[4];
-#pragma unroll
-    for (int q = 0; q < NP; ++q) {
-      const u64 dx = sub2(px[q], X1), dy = sub2(py[q], Y1), dz = sub2(pz[q], Z1);
-      const u64 dd = fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
-      float d[2];
-      unpack2(dd, d[0], d[1]);
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int i = 2 * q + h;
-        hw[i & 3] = __ballot_sync(FULL, d[h] < r2);    // bit L <-> point kbase[w*H + i] + L
-        pt[i] = fminf(d[h], pt[i]);
-      }
-      if ((q & 1) == 1 && lane == 0)                    // four slots' words in one 128-bit store
-        *reinterpret_cast<uint4 *>(wrow + (q - 1) * 2) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-    }
-    if (lane == jr) {
-      my_idx = old;
-      mcx = x1; mcy = y1; mcz = z1;
-    }
-    if (j < m - 1) {
-      // this warp's candidate: (max key, lowest bit-reversed lane among the maxima, first slot equal to the max)
-      const float best = max_tree<H>(pt);
-      const unsigned key = best < 0.f ? 0u : __float_as_uint(best) + 1u;
-      const unsigned M = __reduce_max_sync(FULL, key);
-      unsigned wl = 0xffffffffu;
-      int cand = 0;
-      if (M != 0u) {
-        wl = __reduce_min_sync(FULL, key == M ? rk : 0xffffffffu);
-        float *rw = rec + w * H;
-        if (rk == wl) {
-#pragma unroll
-          for (int i = 0; i < H; i += 4) *reinterpret_cast<float4 *>(rw + i) = make_float4(pt[i], pt[i + 1], pt[i + 2], pt[i + 3]);
-        }
-        __syncwarp();
-        const float mine = lane < H ? rw[lane] : -3.0f;
-        const unsigned eq = __ballot_sync(FULL, __float_as_uint(mine) + 1u == M);
-        cand = kbase[w * H + __ffs(eq) - 1] + brevn((int)wl, 5);
-      }
-      Xchg *xj = xc + (j & 1) * 2;                       // double-buffered by iteration parity: one barrier per iteration
-      if (lane == 0) xj[w] = Xchg{M, wl, cand, 0};
-      __syncthreads();
-      const Xchg a0 = xj[0], a1 = xj[1];
-      // warp 0's slots precede warp 1's in the reference's scan order: on a full tie warp 0 wins
-      const bool take1 = a1.key > a0.key || (a1.key == a0.key && a1.rank < a0.rank);
-      const unsigned Mg = take1 ? a1.key : a0.key;
-      old = Mg == 0u ? 0 : (take1 ? a1.idx : a0.idx);
-      x1 = pts[3 * old + 0];
-      y1 = pts[3 * old + 1];
-      z1 = pts[3 * old + 2];
-    }
-  }
-  __syncthreads();                                       // every hit word of every centre is in W; pts is free from here on
-
-  const int cw = p.m2 > 0 ? 1 : 0;                       // the compaction warp (warp 0 runs level 2 when there is one)
-  {
-    if (w == cw) {
-      // ---- level-1 outputs + ball-query compaction (lane == centre), m <= 32 handled per batch of 32 centres: m == 32 here
-      int *stage = reinterpret_cast<int *>(pts);         // [32][rs] (aliases the cloud copy)
-      const size_t o = (size_t)b * m;
-      if (lane < m) {
-        p.fps_idx[o + lane] = my_idx;
-        float *q = p.new_xyz + (o + lane) * 3;
-        q[0] = mcx; q[1] = mcy; q[2] = mcz;
-      }
-      {
-        const unsigned *wr = W + lane * 36;
-        unsigned nz = 0u;
-        for (int c = 0; c < nchunks; ++c) nz |= (wr[slot_of_chunk[c]] != 0u ? 1u : 0u) << c;
-        if (lane >= m) nz = 0u;
-        int *row = stage + lane * rs;
-        unsigned wv = 0u;
-        int cb = 0, first = 0;
-        for (int s2 = 0; s2 < nsample; ++s2) {
-          if (wv == 0u && nz != 0u) {
-            const int c = __ffs(nz) - 1;
-            nz &= nz - 1u;
-            wv = wr[slot_of_chunk[c]];
-            cb = c << 5;
-          }
-          int v = first;
-          if (wv != 0u) {
-            v = cb + __ffs(wv) - 1;
-            wv &= wv - 1u;
-          }
-          if (s2 == 0) first = v;
-          row[s2] = v;
-        }
-      }
-      __syncwarp();
-      {
-        const int total = m * nsample;
-        int *out = p.ball_idx + o * (size_t)nsample;
-        if (nsample == 32) {
-          for (int e = lane; e < total; e += 32) out[e] = stage[(e >> 5) * rs + lane];
-        } else {
-          for (int e = lane; e < total; e += 32) {
-            const int r = e / nsample, s3 = e - r * nsample;
-            out[e] = stage[r * rs + s3];
-          }
-        }
-      }
-    }
-  }
-  if (w == 0 && p.m2 > 0) {
-    // ---- level 2 on warp 0 (runs beside warp 1's compaction): FPS + ball query over the 32 centres held by the lanes ----------
-    const float qx = mcx, qy = mcy, qz = mcz;
-    const float mag = __fmaf_rn(qz, qz, __fmaf_rn(qx, qx, __fmul_rn(qy, qy)));
-    float t = mag_skipped(mag) ? -2.0f : 1e10f;
-    const float r22 = __fmul_rn(p.radius_2, p.radius_2);
-    const int ns2 = p.nsample2;
-    int old2 = 0;
-    for (int j = 0; j < p.m2; ++j) {
-      const float c1 = __shfl_sync(FULL, qx, old2), c2 = __shfl_sync(FULL, qy, old2), c3 = __shfl_sync(FULL, qz, old2);
-      const float d = sqdist(qx, qy, qz, c1, c2, c3);
-      const unsigned word = __ballot_sync(FULL, d < r22);
-      const size_t o = (size_t)b * p.m2 + j;
-      if (lane == 0) {
-        p.fps_idx2[o] = old2;
-        float *q = p.new_xyz2 + o * 3;
-        q[0] = c1; q[1] = c2; q[2] = c3;
-      }
-      const int cnt = __popc(word);
-      const int first = cnt ? __ffs(word) - 1 : 0;
-      for (int s2 = lane; s2 < ns2; s2 += 32)
-        p.ball_idx2[o * ns2 + s2] = s2 < cnt ? (int)__fns(word, 0, s2 + 1) : first;
-      if (j < p.m2 - 1) {
-        const float d2 = fminf(d, t);
-        t = d2;
-        const unsigned key = d2 < 0.f ? 0u : __float_as_uint(d2) + 1u;
-        const unsigned M = __reduce_max_sync(FULL, key);
-        if (M == 0u) {
-          old2 = 0;
-        } else {
-          const unsigned ww = __reduce_min_sync(FULL, key == M ? rk : 0xffffffffu);
-          old2 = brevn((int)ww, 5);
-        }
-      }
-    }
-  }
-}
-
-int launch2w(const SaSampleParams &p, int B, cudaStream_t st) {
-  size_t smem = (size_t)((3 * p.N + 3) & ~3) * 4 + 64 * 4 + 32 * 36 * 4 + 32 * 4 + 4 * sizeof(Xchg);
-  const size_t stage = (size_t)32 * (p.nsample | 1) * 4;     // aliases the cloud copy: must fit into it
-  if (stage > (size_t)3 * p.N * 4) return -1;
-  if (smem > 48 * 1024) {
-    int rc = sv::cuda_status(cudaFuncSetAttribute(sa_sample2w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (rc) return rc;
-  }
-  sa_sample2w_kernel<<<B, 64, smem, st>>>(p);
-  return sv::after_launch();
-}
-
 template <int SPT>
 int launch(const SaSampleParams &p, int B, cudaStream_t st) {
   const size_t smem = (size_t)((3 * p.N + 3) & ~3) * 4 + 64 * 4 + 32 * 33 * 4 + 32 * 4 +
@@ -575,10 +345,6 @@ extern "C" int sv_sa_sample_f32(const float *xyz, int B, int N, int m, float rad
   if (p.spt <= 4) return launch<4>(p, B, st);
   if (p.spt <= 8) return launch<8>(p, B, st);
   if (p.spt <= 16) return launch<16>(p, B, st);
-  if (p.spt == 32 && m == 32 && p.nsample <= 64) {   // the GPS shape (N = 1024, 32 centres): two warps per cloud
-    const int rc = launch2w(p, B, st);
-    if (rc >= 0) return rc;
-  }
   if (p.spt <= 32) return launch<32>(p, B, st);
   return SV_ERR_INVALID_ARG;
 }
