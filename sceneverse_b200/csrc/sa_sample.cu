@@ -112,7 +112,10 @@ __global__ void __launch_bounds__(32) sa_sample_kernel(const SaSampleParams p) {
   int *slot_of_chunk = kbase + 32;                             // [32] slot holding points [32c, 32c+32)
   unsigned *W = reinterpret_cast<unsigned *>(slot_of_chunk + 32);  // [32][33] hit words: row = centre, col = slot
   float *rec = reinterpret_cast<float *>(W + 32 * 33);         // [32] winner lane's running distances
-  int *stage = reinterpret_cast<int *>(rec + 32);              // [32][rs]
+  // [32][rs] compaction staging; with a single batch of centres (m <= 32) the cloud copy is dead by then (the last FPS
+  // iteration selects nothing), so the staging rows alias it: 17 KB instead of 21 KB per cloud = 12 instead of 10 clouds per SM
+  const bool alias_stage = m <= 32 && (size_t)32 * rs <= (size_t)n3;
+  int *stage = alias_stage ? reinterpret_cast<int *>(pts) : reinterpret_cast<int *>(rec + 32);
 
   stage_floats(pts, p.xyz + (size_t)b * n3, n3, lane, 32);
   if (lane < p.spt) {
@@ -307,8 +310,9 @@ __global__ void __launch_bounds__(32) sa_sample_kernel(const SaSampleParams p) {
 
 template <int SPT>
 int launch(const SaSampleParams &p, int B, cudaStream_t st) {
+  const bool alias_stage = p.m <= 32 && (size_t)32 * (p.nsample | 1) <= (size_t)3 * p.N;
   const size_t smem = (size_t)((3 * p.N + 3) & ~3) * 4 + 64 * 4 + 32 * 33 * 4 + 32 * 4 +
-                      (size_t)32 * (p.nsample | 1) * 4;
+                      (alias_stage ? 0 : (size_t)32 * (p.nsample | 1) * 4);
   auto kern = sa_sample_kernel<SPT>;
   if (smem > 48 * 1024) {
     int rc = sv::cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
