@@ -371,8 +371,10 @@ def test_rerouted_bert_matches_huggingface_bert_gpu():
         if isinstance(m, torch.nn.Dropout):
             m.p = 0.0
     (ref(ids, mask).last_hidden_state * proj * valid[..., None]).sum().backward()
+    # the key bias gradient is mathematically zero (softmax is invariant to a per-query shift): compare against a floor
+    scale = max(q.grad.abs().max().item() for n, q in ref.named_parameters() if "pooler" not in n)
     for (n, p), (_, q) in zip(enc.model.named_parameters(), ref.named_parameters()):
         if "pooler" in n:
             continue
-        rel = (p.grad.float() - q.grad).abs().max().item() / (q.grad.abs().max().item() + 1e-6)
+        rel = (p.grad.float() - q.grad).abs().max().item() / (q.grad.abs().max().item() + 2e-3 * scale)
         assert rel < 8e-2, (n, rel)
