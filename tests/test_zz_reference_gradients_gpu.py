@@ -14,7 +14,7 @@ GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 
 
 # bounds = 2x the deviation measured on the B200 (profiles/r2_parity_bf16_grads.json)
-LOSS_TOL, NORM_TOL, FLOOR = 2e-2, 5e-2, 1e-3
+LOSS_TOL, NORM_TOL, FLOOR = 7e-3, 8.5e-2, 1e-3    # measured: losses <= 3.3e-3, worst gradient-norm deviation 4.2e-2
 
 
 def load(m, seed):
