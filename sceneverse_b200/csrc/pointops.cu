@@ -710,18 +710,27 @@ int sv_group_points_f32(const float *points, const int *idx, int B, int C, int N
   if (B < 0 || C < 0 || N < 0 || NP < 0 || NS < 0) return SV_ERR_INVALID_ARG;
   const long long E = (long long)NP * NS;
   if (B == 0 || C == 0 || E == 0) return SV_OK;
-  if (!points || !idx || !out || E > 0x7fffffffLL || B > 65535) return SV_ERR_INVALID_ARG;
+  if (!points || !idx || !out || E > 0x7fffffffLL) return SV_ERR_INVALID_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   const bool vec = (E % 4 == 0) && ((reinterpret_cast<uintptr_t>(idx) & 15) == 0) &&
                    ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-  if (vec) {
-    dim3 grid((unsigned)((E / 4 + 255) / 256), B);
-    group_points_kernel<true><<<grid, 256, 0, st>>>(points, idx, C, N, (int)E, out);
-  } else {
-    dim3 grid((unsigned)((E + 255) / 256), B);
-    group_points_kernel<false><<<grid, 256, 0, st>>>(points, idx, C, N, (int)E, out);
+  // the batch rides on grid.y (<= 65535): larger batches go out in chunks (the reference kernels have no batch limit)
+  for (int b0 = 0; b0 < B; b0 += 65535) {
+    const int nb = B - b0 < 65535 ? B - b0 : 65535;
+    const float *pp = points + (size_t)b0 * C * N;
+    const int *ii = idx + (size_t)b0 * E;
+    float *oo = out + (size_t)b0 * C * E;
+    if (vec) {
+      dim3 grid((unsigned)((E / 4 + 255) / 256), nb);
+      group_points_kernel<true><<<grid, 256, 0, st>>>(pp, ii, C, N, (int)E, oo);
+    } else {
+      dim3 grid((unsigned)((E + 255) / 256), nb);
+      group_points_kernel<false><<<grid, 256, 0, st>>>(pp, ii, C, N, (int)E, oo);
+    }
+    const int rc = sv::after_launch();
+    if (rc) return rc;
   }
-  return sv::after_launch();
+  return SV_OK;
 }
 
 int sv_group_points_grad_f32(const float *grad_out, const int *idx, int B, int C, int N, int NP, int NS,
@@ -735,10 +744,16 @@ int sv_group_points_grad_f32(const float *grad_out, const int *idx, int B, int C
     if (rc) return rc;
   }
   if (B == 0 || C == 0 || E == 0) return SV_OK;
-  if (!grad_out || !idx || E > 0x7fffffffLL || B > 65535) return SV_ERR_INVALID_ARG;
-  dim3 grid((unsigned)((E + 255) / 256), B);
-  group_points_grad_kernel<<<grid, 256, 0, st>>>(grad_out, idx, C, N, (int)E, grad_points);
-  return sv::after_launch();
+  if (!grad_out || !idx || E > 0x7fffffffLL) return SV_ERR_INVALID_ARG;
+  for (int b0 = 0; b0 < B; b0 += 65535) {
+    const int nb = B - b0 < 65535 ? B - b0 : 65535;
+    dim3 grid((unsigned)((E + 255) / 256), nb);
+    group_points_grad_kernel<<<grid, 256, 0, st>>>(grad_out + (size_t)b0 * C * E, idx + (size_t)b0 * E, C, N, (int)E,
+                                                   grad_points + (size_t)b0 * C * N);
+    const int rc = sv::after_launch();
+    if (rc) return rc;
+  }
+  return SV_OK;
 }
 
 int sv_gather_points_f32(const float *points, const int *idx, int B, int C, int N, int M, float *out, void *stream) {
@@ -754,20 +769,32 @@ int sv_three_nn_f32(const float *unknown, const float *known, int B, int n, int 
                     void *stream) {
   if (B < 0 || n < 0 || m < 0) return SV_ERR_INVALID_ARG;
   if (B == 0 || n == 0) return SV_OK;
-  if (!unknown || (!known && m > 0) || !dist2 || !idx || B > 65535) return SV_ERR_INVALID_ARG;
-  dim3 grid((n + 255) / 256, B);
-  three_nn_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(unknown, known, n, m, dist2, idx);
-  return sv::after_launch();
+  if (!unknown || (!known && m > 0) || !dist2 || !idx) return SV_ERR_INVALID_ARG;
+  for (int b0 = 0; b0 < B; b0 += 65535) {
+    const int nb = B - b0 < 65535 ? B - b0 : 65535;
+    dim3 grid((n + 255) / 256, nb);
+    three_nn_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(unknown + (size_t)b0 * n * 3, known ? known + (size_t)b0 * m * 3 : known, n,
+                                                            m, dist2 + (size_t)b0 * n * 3, idx + (size_t)b0 * n * 3);
+    const int rc = sv::after_launch();
+    if (rc) return rc;
+  }
+  return SV_OK;
 }
 
 int sv_three_interpolate_f32(const float *points, const int *idx, const float *weight, int B, int c, int m, int n,
                              float *out, void *stream) {
   if (B < 0 || c < 0 || m < 0 || n < 0) return SV_ERR_INVALID_ARG;
   if (B == 0 || c == 0 || n == 0) return SV_OK;
-  if (!points || !idx || !weight || !out || B > 65535) return SV_ERR_INVALID_ARG;
-  dim3 grid((n + 255) / 256, B);
-  three_interpolate_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(points, idx, weight, c, m, n, out);
-  return sv::after_launch();
+  if (!points || !idx || !weight || !out) return SV_ERR_INVALID_ARG;
+  for (int b0 = 0; b0 < B; b0 += 65535) {
+    const int nb = B - b0 < 65535 ? B - b0 : 65535;
+    dim3 grid((n + 255) / 256, nb);
+    three_interpolate_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(points + (size_t)b0 * c * m, idx + (size_t)b0 * n * 3,
+                                                                     weight + (size_t)b0 * n * 3, c, m, n, out + (size_t)b0 * c * n);
+    const int rc = sv::after_launch();
+    if (rc) return rc;
+  }
+  return SV_OK;
 }
 
 int sv_three_interpolate_grad_f32(const float *grad_out, const int *idx, const float *weight, int B, int c, int n,
@@ -780,10 +807,16 @@ int sv_three_interpolate_grad_f32(const float *grad_out, const int *idx, const f
     if (rc) return rc;
   }
   if (B == 0 || c == 0 || n == 0) return SV_OK;
-  if (!grad_out || !idx || !weight || B > 65535) return SV_ERR_INVALID_ARG;
-  dim3 grid((n + 255) / 256, B);
-  three_interpolate_grad_kernel<<<grid, 256, 0, st>>>(grad_out, idx, weight, c, n, m, grad_points);
-  return sv::after_launch();
+  if (!grad_out || !idx || !weight) return SV_ERR_INVALID_ARG;
+  for (int b0 = 0; b0 < B; b0 += 65535) {
+    const int nb = B - b0 < 65535 ? B - b0 : 65535;
+    dim3 grid((n + 255) / 256, nb);
+    three_interpolate_grad_kernel<<<grid, 256, 0, st>>>(grad_out + (size_t)b0 * c * n, idx + (size_t)b0 * n * 3,
+                                                        weight + (size_t)b0 * n * 3, c, n, m, grad_points + (size_t)b0 * c * m);
+    const int rc = sv::after_launch();
+    if (rc) return rc;
+  }
+  return SV_OK;
 }
 
 }  // extern "C"

@@ -180,3 +180,23 @@ def test_matches_reference_cuda_golden(ext, path):
         np.testing.assert_array_equal(got.cpu().numpy(), z["out"])
     elif op == "group_points":
         np.testing.assert_array_equal(ext.group_points(dev(z["points"]), dev(z["idx"])).cpu().numpy(), z["out"])
+
+
+@pytest.mark.gpu
+def test_batches_beyond_the_grid_y_limit():
+    """group / gather / three_interpolate put the batch on grid.y (<= 65535): larger batches are chunked, as the reference kernels
+    (grid = (b, c)) have no such limit."""
+    from sceneverse_b200.pointnet2 import _ext
+    B = 70001
+    g = torch.Generator(device="cuda").manual_seed(0)
+    pts = torch.randn(B, 2, 5, device="cuda", generator=g)
+    idx = torch.randint(0, 5, (B, 3, 2), device="cuda", generator=g, dtype=torch.int32)
+    out = _ext.group_points(pts, idx)
+    want = torch.gather(pts[:, :, None, :].expand(-1, -1, 3, -1), 3, idx.long()[:, None].expand(-1, 2, -1, -1))
+    assert torch.equal(out, want)
+    go = torch.randn(B, 2, 3, 2, device="cuda", generator=g)
+    gp = _ext.group_points_grad(go, idx, 5)
+    ref = torch.zeros(B, 2, 5, device="cuda").scatter_add_(2, idx.long().view(B, 1, 6).expand(-1, 2, -1), go.view(B, 2, 6))
+    assert (gp - ref).abs().max().item() < 1e-5
+    gi = torch.randint(0, 5, (B, 3), device="cuda", generator=g, dtype=torch.int32)
+    assert torch.equal(_ext.gather_points(pts, gi), torch.gather(pts, 2, gi.long()[:, None].expand(-1, 2, -1)))
