@@ -217,6 +217,30 @@ int sv_adamw_flat(float *params, float *exp_avg, float *exp_avg_sq, const float 
                   const void *segments, int nseg, float max_norm, const float *lr_factor, const long long *step, float base_lr,
                   float beta1, float beta2, float eps, float *scratch, float *norm_out, void *stream);
 
+/* ---- train-mode PointNet++ set abstraction in channels-last form (config C2: ObjCls pre-training with a trainable backbone) ----
+ * A grouped tensor is the row matrix X[(b, centre, sample)][channel] in bf16: the 1x1 convolutions are sv_linear_*_bf16 (no bias),
+ * BatchNorm2d with BATCH statistics is a column statistic over the rows, the neighbourhood max is a max over ns consecutive rows.
+ * Reference: pointnet2_utils.py:291-373 (QueryAndGroup / GroupAll), pytorch_utils.py:11-36,67-120 (SharedMLP: Conv2d + BatchNorm2d +
+ * ReLU), pointnet2_modules.py:70-73 (max_pool2d over nsample).
+ * group_rows: X (B*np*ns, Cp) bf16, Cp % 8 == 0, Cp >= 3 + C: [xyz[idx] - centre | feat[idx] | 0]; centre NULL = raw xyz (GroupAll);
+ * idx (B,np,ns) i32 or NULL (GroupAll: every point in order, np = 1, ns = N); feat (B,N,C) point-major f32 | bf16.
+ * group_rows_grad: dfeat (B,N,C) f32 (zeroed here) += dX[:, 3:3+C] scattered by idx. */
+int sv_pn_group_rows(const float *xyz, const float *centre, const void *feat, int feat_bf16, const int *idx, int B, int N, int C,
+                     int np, int ns, int Cp, void *X, void *stream);
+int sv_pn_group_rows_grad(const void *dX, const int *idx, int B, int N, int C, int np, int ns, int Cp, float *dfeat, void *stream);
+/* BatchNorm (batch statistics over the R rows, biased variance) + ReLU: y, out (R,C) bf16; mean, rstd (C) f32 out; var_unbiased (C)
+ * f32 out (may be NULL; for the running estimate); scratch: sv_pn_scratch_floats(C).  Backward: dy = d(out)/d(y) applied to dout,
+ * dgamma / dbeta (C) f32 overwritten or accumulated. */
+int sv_pn_scratch_floats(int C);
+int sv_pn_bn_relu_fwd(const void *y, long long R, int C, const float *gamma, const float *beta, float eps, float *mean, float *rstd,
+                      float *var_unbiased, void *out, float *scratch, void *stream);
+int sv_pn_bn_relu_bwd(const void *y, const void *dout, long long R, int C, const float *gamma, const float *beta, const float *mean,
+                      const float *rstd, void *dy, float *dgamma, float *dbeta, int accumulate, float *scratch, void *stream);
+/* out[g][c] = max over the ns rows of group g, arg = index of the first maximum (bytes, ns <= 255); grad: gx[g*ns+s][c] = gout[g][c]
+ * where s == arg, else 0. */
+int sv_pn_rowgroup_max(const void *x, long long G, int ns, int C, void *out, unsigned char *arg, void *stream);
+int sv_pn_rowgroup_max_grad(const void *gout, const unsigned char *arg, long long G, int ns, int C, void *gx, void *stream);
+
 /* L2-normalise + all-gather fused over NVLink peer memory (reference: contra_loss.py:58-64,86-91 + dist_utils.py:131-149).
  * a, b: local (n,D) f32.  peer_bufs[world] / peer_signals[world]: DEVICE arrays of device pointers into a symmetric
  * allocation mapped on every rank: buffer = [2 parities][2 tensors][world*n][D] f32, signal = >= world uint32 words

@@ -20,7 +20,7 @@ NVCC_FLAGS = [
 # library name -> sources (relative to csrc/)
 LIBS = {
     "libsvpointops.so": ["pointops.cu", "sa_sample.cu", "fps_coop.cu", "scene_prep.cu"],
-    "libsvgps.so": ["gps_common.cu", "tc05_selftest.cu", "sa_mlp.cu", "gemm.cu", "attention.cu", "attention_bwd.cu", "pairwise_locs.cu", "cross_entropy.cu", "norm_allgather.cu", "layer_norm.cu", "colsum.cu", "train_ops.cu", "mma_bench.cu"],
+    "libsvgps.so": ["gps_common.cu", "tc05_selftest.cu", "sa_mlp.cu", "gemm.cu", "attention.cu", "attention_bwd.cu", "pairwise_locs.cu", "cross_entropy.cu", "norm_allgather.cu", "layer_norm.cu", "colsum.cu", "train_ops.cu", "mma_bench.cu", "pn_train.cu"],
 }
 
 

@@ -186,6 +186,11 @@ class PointNetPP(nn.Module):
         """@param features: (B*N_objects, N_points, 3 + C)  ->  (B*N_objects, D)"""
         if self.fused_available(features):
             return self.forward_fused(features)
+        from .. import pn_train
+        if pn_train.available(features, self):
+            # trainable backbone under bf16 autocast (ObjCls pre-training): channels-last native path — tcgen05 GEMMs for the
+            # 1x1 convolutions, batch-statistic BatchNorm / max kernels of csrc/pn_train.cu
+            return pn_train.forward(self, features)
         return self.forward_generic(features)
 
     def forward_generic(self, pc):

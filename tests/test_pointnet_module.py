@@ -162,3 +162,41 @@ def test_objcls_step_trains_pointnet_through_native_grads():
     g1 = grads["point_feature_extractor.encoder.1.mlps.0.layer0.conv.weight"].float()
     g2 = pn.encoder[1].mlps[0].layer0.conv.weight.grad.float()
     assert (g1 - g2).abs().max().item() <= 0.1 * g2.abs().max().item() + 1e-6
+
+
+@pytest.mark.gpu
+def test_trainable_backbone_native_path_matches_the_generic_operator_sequence():
+    """Config C2 (ObjCls, trainable PointNet++, train-mode BatchNorm): the channels-last native path (tcgen05 GEMMs for the 1x1
+    convolutions + csrc/pn_train.cu batch-statistic BatchNorm / max kernels, bf16) against the reference operator sequence in
+    fp32 (torch Conv2d / BatchNorm2d / max_pool2d on the same native point ops): output, every parameter gradient and the
+    BatchNorm running statistics."""
+    import copy
+    from sceneverse_b200 import pn_train
+    from sceneverse_b200.modules.pointnet import GPS_SPEC, PointNetPP
+    torch.manual_seed(0)
+    net = PointNetPP(**GPS_SPEC)
+    net.load_state_dict(weights.synthetic_state_dict(net, 0))
+    net = net.cuda().train()
+    ref = copy.deepcopy(net)
+    x = torch.from_numpy(synthetic.object_batch(3, 48, 1024, pad_fraction=0.0)).cuda()
+    go = torch.randn(48, 768, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        assert pn_train.available(x, net)
+        y = net(x)
+    y.float().backward(go)
+    yr = ref.forward_generic(x)                      # fp32, no autocast: the reference operator sequence
+    yr.backward(go)
+    err = (y.float() - yr).abs().max().item() / yr.abs().max().item()
+    assert err < 4e-2, err
+    worst = {}
+    for (n, p), (_, q) in zip(net.named_parameters(), ref.named_parameters()):
+        assert p.grad is not None, n
+        e = (p.grad.float() - q.grad).abs().max().item() / (q.grad.abs().max().item() + 1e-8)
+        worst[n] = e
+        assert e < 0.12, (n, e)
+    for (n, b1), (_, b2) in zip(net.named_buffers(), ref.named_buffers()):
+        if "running" in n:
+            assert (b1 - b2).abs().max().item() <= 3e-2 * (b2.abs().max().item() + 1e-3), n
+        elif "num_batches_tracked" in n:
+            assert int(b1) == int(b2) == 1
+    print("TRAINABLE_PN output err", err, "worst grad err", max(worst.values()))
