@@ -195,11 +195,84 @@ def test_trainable_backbone_native_path_matches_the_generic_operator_sequence():
         cos = torch.nn.functional.cosine_similarity(p.grad.float().flatten(), q.grad.flatten(), dim=0).item()
         worst[n] = (round(e, 4), round(cos, 5))
     print("TRAINABLE_PN grads", worst)
+    # behind the last neighbourhood max the two paths route the gradient identically: tight agreement there; in front of a max
+    # taken over bf16 values ties are frequent and "first maximum" picks a different (equally valid) point than the fp32 run,
+    # so the earlier layers are only required to point the same way
+    for n in ("fc.weight", "fc.bias", "encoder.2.mlps.0.layer2.bn.bn.weight", "encoder.2.mlps.0.layer2.bn.bn.bias"):
+        assert worst[n][1] > 0.999 and worst[n][0] < 0.1, (n, worst[n])
     for n, (e, cos) in worst.items():
-        assert cos > 0.97, (n, e, cos)
+        assert cos > 0.8, (n, e, cos)
     for (n, b1), (_, b2) in zip(net.named_buffers(), ref.named_buffers()):
         if "running" in n:
             assert (b1 - b2).abs().max().item() <= 3e-2 * (b2.abs().max().item() + 1e-3), n
         elif "num_batches_tracked" in n:
             assert int(b1) == int(b2) == 1
     print("TRAINABLE_PN output err", err)
+
+
+@pytest.mark.gpu
+def test_trainable_backbone_building_blocks_match_torch_on_the_same_operands():
+    """Unit parity of the three autograd Functions of the train-mode path against torch formulations fed with the SAME bf16
+    operands (so that rounding / tie-breaking of the inputs is shared): 1x1 conv + batch-statistic BatchNorm + ReLU, the
+    neighbourhood max, and the channels-last grouping with its scatter-add gradient."""
+    import torch.nn.functional as F
+    from sceneverse_b200 import pn_train
+    g = torch.Generator(device="cuda").manual_seed(0)
+
+    def rel(a, b):
+        return (a.float() - b.float()).abs().max().item() / (b.float().abs().max().item() + 1e-9)
+    # --- conv1x1 + BN(batch statistics) + ReLU -----------------------------------------------------------------------------
+    R, Cin, Cout = 8192, 67, 128
+    Xb = torch.zeros(R, 72, device="cuda", dtype=torch.bfloat16)
+    Xb[:, :Cin] = torch.randn(R, Cin, device="cuda", generator=g).bfloat16()
+    X = Xb.clone().requires_grad_(True)
+    W = (torch.randn(Cout, Cin, 1, 1, device="cuda", generator=g) * 0.2).requires_grad_(True)
+    gam = (1 + 0.2 * torch.randn(Cout, device="cuda", generator=g)).requires_grad_(True)
+    bet = (0.2 * torch.randn(Cout, device="cuda", generator=g)).requires_grad_(True)
+    go = torch.randn(R, Cout, device="cuda", generator=g).bfloat16()
+    out, stats = pn_train._ConvBNReLUFn.apply(X, W, gam, bet, 1e-5)
+    out.backward(go)
+    Xr = Xb[:, :Cin].float().requires_grad_(True)
+    Wr = W.detach().bfloat16().float().reshape(Cout, Cin).requires_grad_(True)
+    gr, br = gam.detach().clone().requires_grad_(True), bet.detach().clone().requires_grad_(True)
+    yr = (Xr @ Wr.t()).bfloat16().float() + ((Xr @ Wr.t()) - (Xr @ Wr.t()).detach())      # the kernel stores Y in bf16
+    ref = torch.relu(F.batch_norm(yr, None, None, gr, br, True, 0.0, 1e-5))
+    ref.backward(go.float())
+    assert rel(out, ref) < 1e-2
+    assert rel(stats[0], yr.mean(0)) < 1e-3 and rel(stats[2], yr.var(0, unbiased=True)) < 2e-3
+    assert rel(X.grad[:, :Cin], Xr.grad) < 2.5e-2 and rel(W.grad.reshape(Cout, Cin), Wr.grad) < 2.5e-2
+    assert rel(gam.grad, gr.grad) < 1e-2 and rel(bet.grad, br.grad) < 1e-2
+    # --- neighbourhood max (tie-free values) ---------------------------------------------------------------------------------
+    G, ns, C = 300, 32, 64
+    base = torch.rand(G * ns, C, device="cuda", generator=g).argsort(0).float() / (G * ns)      # all distinct per column
+    xv = base.bfloat16().float()
+    keep = torch.ones_like(xv, dtype=torch.bool)
+    x = xv.bfloat16().requires_grad_(True)
+    o = pn_train._RowGroupMaxFn.apply(x, ns)
+    gm = torch.randn(G, C, device="cuda", generator=g).bfloat16()
+    o.backward(gm)
+    xr = x.detach().float().requires_grad_(True)
+    orr = xr.view(G, ns, C).amax(1)
+    assert torch.equal(o.float(), orr)
+    # gradient: the whole group gradient lands on maximal entries (ties share rows in torch; here exactly one row gets it)
+    assert torch.allclose(x.grad.float().view(G, ns, C).sum(1), gm.float(), atol=1e-6)
+    assert ((x.grad.float() != 0) <= (x.detach().float().view(G, ns, C) == orr[:, None]).view(G * ns, C)).all()
+    # --- channels-last grouping + scatter-add gradient ---------------------------------------------------------------------------
+    B, N, Cf, np_, ns = 5, 200, 13, 7, 9
+    xyz = torch.randn(B, N, 3, device="cuda", generator=g)
+    cen = torch.randn(B, np_, 3, device="cuda", generator=g)
+    feat = torch.randn(B, N, Cf, device="cuda", generator=g).requires_grad_(True)
+    idx = torch.randint(0, N, (B, np_, ns), device="cuda", generator=g, dtype=torch.int32)
+    Xg = pn_train._GroupRowsFn.apply(xyz, cen, feat, idx, np_, ns)
+    assert Xg.shape == (B * np_ * ns, 16)
+    il = idx.long()
+    gx = torch.gather(xyz[:, None].expand(-1, np_, -1, -1), 2, il[..., None].expand(-1, -1, -1, 3)) - cen[:, :, None]
+    gf = torch.gather(feat[:, None].expand(-1, np_, -1, -1), 2, il[..., None].expand(-1, -1, -1, Cf))
+    want = torch.cat([gx, gf], -1).reshape(-1, 3 + Cf)
+    assert rel(Xg[:, :16].float()[:, :3 + Cf], want.detach()) < 8e-3 and (Xg[:, 3 + Cf:] == 0).all()
+    gX = torch.randn(Xg.shape, device="cuda", generator=g).bfloat16()
+    Xg.backward(gX, retain_graph=False)
+    got = feat.grad.clone()
+    feat.grad = None
+    gf.backward(gX[:, 3:3 + Cf].float().reshape(B, np_, ns, Cf))
+    assert rel(got, feat.grad) < 1e-5
