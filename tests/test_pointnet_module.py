@@ -235,7 +235,8 @@ def test_trainable_backbone_building_blocks_match_torch_on_the_same_operands():
     Xr = Xb[:, :Cin].float().requires_grad_(True)
     Wr = W.detach().bfloat16().float().reshape(Cout, Cin).requires_grad_(True)
     gr, br = gam.detach().clone().requires_grad_(True), bet.detach().clone().requires_grad_(True)
-    yr = (Xr @ Wr.t()).bfloat16().float() + ((Xr @ Wr.t()) - (Xr @ Wr.t()).detach())      # the kernel stores Y in bf16
+    y0 = Xr @ Wr.t()
+    yr = y0 + (y0.detach().bfloat16().float() - y0.detach())      # the kernel stores Y in bf16 (straight-through rounding)
     ref = torch.relu(F.batch_norm(yr, None, None, gr, br, True, 0.0, 1e-5))
     ref.backward(go.float())
     assert rel(out, ref) < 1e-2
