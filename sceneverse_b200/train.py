@@ -333,7 +333,12 @@ class PretrainStep:
         return tuple(sum(e[i].elapsed_time(e[i + 1]) for e in ev) / steps for i in range(3))
 
     def step(self, data_dict):
-        """data_dict: tensors already on self.device. Returns the (detached) total loss tensor — no host sync."""
+        """data_dict: tensors already on self.device. Returns the (detached) total loss tensor — no host sync.
+        Graph mode: (1) the FIRST call runs the un-timed set-up on its batch — one probing forward/backward, three eager
+        optimisation steps (they allocate gradient / optimizer state outside the graph pool), the capture, and the first replay —
+        i.e. four parameter updates on that batch, unlike the reference's one step per batch; feed a throw-away batch first if
+        that matters.  (2) the returned tensor is the graph's STATIC loss buffer, overwritten by the next replay: read it
+        (`.item()` / `.clone()`) before calling step() again if the value has to be kept."""
         if self.graph_mode:
             return self._graph_step(data_dict)
         if not self.probed:
