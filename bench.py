@@ -481,10 +481,11 @@ def main():
     phases = equal_work = None
     if world > 1 and getattr(ps, "dp_graph", False) and ps.graph_opt is not None:
         # where the data-parallel step goes when nothing is overlapped: graph(forward+backward) | NCCL all-reduce | graph(clip+AdamW)
-        pt = torch.tensor(ps.phase_times(dict(resident[0]), steps=5), device=device, dtype=torch.float64)
+        pt = torch.tensor(ps.phase_times(dict(resident[0]), steps=10), device=device, dtype=torch.float64)
         dist.all_reduce(pt, op=dist.ReduceOp.MAX)
         phases = {"ms_fwd_bwd": float(pt[0]), "ms_allreduce": float(pt[1]), "ms_opt": float(pt[2]),
-                  "note": "un-overlapped path, 5 extra steps after the timed region, max over ranks"}
+                  "note": "un-overlapped path, 3 + 10 extra steps after the timed region, CUDA events, max over ranks; the exchange kernel inside "
+                          "forward+backward waits for the slowest peer, so rank skew shows up there"}
     if world == 1 and args.workload == "gps_pretrain" and not args.no_equal_work and not args.no_graph:
         # the step ONE rank of a data-parallel job executes (distributed autograd semantics of common/dist_utils.py:131-149: the
         # between-batch negatives carry no gradient, so the scene-caption text-encoder backward disappears) — the equal-work

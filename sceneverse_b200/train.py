@@ -316,10 +316,13 @@ class PretrainStep:
         """(ms_fwd_bwd, ms_allreduce, ms_opt) of the NON-overlapped data-parallel step (graph | NCCL | graph), CUDA events on
         the current stream; the parameters do advance (these are real steps)."""
         assert self.dp_graph and self.graph is not None and self.graph_opt is not None
-        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(steps)]
+        warm = 3                      # un-timed: the ranks fall into step (the exchange kernel waits for the slowest peer)
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(warm + steps)]
         for k, dst in self.static_batch.items():
             if data_dict[k].data_ptr() != dst.data_ptr():
                 dst.copy_(data_dict[k], non_blocking=True)
+        torch.cuda.synchronize(self.device)
+        dist.barrier()
         for e in ev:
             e[0].record()
             self.graph.replay()
@@ -330,7 +333,7 @@ class PretrainStep:
             e[3].record()
             self._advance_lr()
         torch.cuda.synchronize(self.device)
-        return tuple(sum(e[i].elapsed_time(e[i + 1]) for e in ev) / steps for i in range(3))
+        return tuple(sum(e[i].elapsed_time(e[i + 1]) for e in ev[warm:]) / steps for i in range(3))
 
     def step(self, data_dict):
         """data_dict: tensors already on self.device. Returns the (detached) total loss tensor — no host sync.
