@@ -55,12 +55,20 @@ int sv_gemm_bf16_ex(const void *A, int lda, int a_transposed, const void *B, int
 
 /* Micro-benchmark (profiling only): SM cycles for `iters` x 4 tcgen05.mma (M = 128, N, K = 16 each) issued back to back on
  * shared-memory-resident operands, per block, by operand layout (a_mn / b_mn = 1: MN-major, transposed operand).
- * cycles_out: `blocks` int64 on the device. */
+ * cycles_out: 2 x `blocks` int64 on the device — SM cycles, then nanoseconds (globaltimer) of each block's issue loop.
+ * Bits 1.. of a_mn are profiling flags: 1 = random operand bits instead of zeros, 2 = commit every four MMAs to a ring of
+ * four barriers and wait for the group issued four groups earlier (the GEMM main loop's stage hand-shake). */
 int sv_mma_bench(int N, int a_mn, int b_mn, int iters, int blocks, long long *cycles_out, void *stream);
 
 /* Kernel selection of the GEMM family (tests / benchmarks): 0 = heuristic (default), 1 = single-CTA tiles (M = 128 per MMA),
- * 2 = CTA pairs (cta_group::2, M = 256 per MMA, each CTA stages half of the B tile) wherever M > 128. */
+ * 2 = CTA pairs (cta_group::2, M = 256 per MMA, each CTA stages half of the B tile) wherever M > 128.
+ * Bits 8.. are profiling switches that make the RESULT GARBAGE (timing only): 1 = the epilogue skips its body,
+ * 2 = the producer skips its TMA loads. */
 int sv_gemm_force_ctas(int ctas);
+
+/* Profiling: while `buf` (device, [grid][8] int64) is non-null every GEMM launch writes, per CTA, the MMA-issuing thread's
+ * {loop cycles, cycles waiting for operands, cycles waiting for a free accumulator, k-steps issued, clock at start, at end}. */
+int sv_gemm_profile(long long *buf);
 
 /* ---- the three GEMMs of a linear layer y = x W^T + b with their fused epilogues (same tcgen05 kernel family) ------
  * Replace F.linear and its autograd (AddmmBackward: mm, mm, sum) for every nn.Linear of the attention stack, BERT and the

@@ -110,6 +110,7 @@ _GPS_SIGS = {
     "sv_colsum": [c_void_p, ctypes.c_longlong, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
     "sv_colsum_scratch_floats": [c_int],
     "sv_gemm_force_ctas": [c_int],
+    "sv_gemm_profile": [c_void_p],
     "sv_mma_bench": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "sv_linear_fwd_bf16": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_float, ctypes.c_ulonglong,
                            c_void_p, c_int, c_int, c_void_p, c_void_p],

@@ -43,6 +43,8 @@ constexpr int EPI_FWD = 0, EPI_DGRAD = 1, EPI_WGRAD = 2;
 
 struct GemmArgs {
   int M, N, K;
+  int dbg = 0;              // profiling switches (sv_gemm_force_ctas bits 8..): 1 = epilogue skips its body, 2 = producer skips TMA
+  long long *prof = nullptr;  // profiling (sv_gemm_profile): [gridDim.x][8] cycle counters of the role threads, or null
   const float *bias;        // [N] or null (FWD)
   const void *residual;     // [M,N] same dtype as out, or null (FWD; added after activation / dropout)
   void *out;                // [M,N] (or [M/rowmax,N] when rowmax > 0)
@@ -201,6 +203,30 @@ __device__ __forceinline__ void tma_load_2d_pair(void *dst, const CUtensorMap *m
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar_cluster_addr)
       : "memory");
 }
+// warp-converged forms (every lane executes, elect.sync picks the issuing lane): TMA tile load crediting `bar_addr` (a
+// shared::cluster address — the own CTA's barrier, or with CTA pairs the leader's) and the expect_tx arrival
+template <int CTAS>
+__device__ __forceinline__ void tma_load_2d_elect(uint32_t dst_smem, const CUtensorMap *map, int c0, int c1, uint32_t bar_addr) {
+  if (CTAS == 1) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+        "@q cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n\t}"
+        ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar_addr)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+        "@q cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n\t}"
+        ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar_addr)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void expect_tx_elect(uint32_t bar_smem_addr, uint32_t bytes) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+      "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(bar_smem_addr), "r"(bytes)
+      : "memory");
+}
 template <int CTAS>
 __device__ __forceinline__ void mma_bf16_g(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   if (CTAS == 1) {
@@ -307,82 +333,95 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
 
   if (warp == 0) {
     // ------------------------------- TMA producer (every CTA stages its own rows of A and its share of B) -------------
-    if (lane == 0) {
-      uint32_t it = 0;
+    // The whole warp runs the loop converged; only the TMA / expect_tx instructions are predicated on elect.sync, so the
+    // coordinates and addresses stay warp-uniform (see tc05.cuh: warp-converged issue).
+    {
+      const uint32_t full0 = smem_u32(full), sA0 = smem_u32(sA), sB0 = smem_u32(sB);
+      const uint32_t fb0 = CTAS == 2 ? map_to_rank(full0, 0) : full0;   // the leader's barriers (CTA pairs)
+      uint32_t s = 0, ph = 1;   // waiting on parity 1 of a fresh barrier returns at once: the first pass finds every slot free
       for (int item = unit; item < n_items; item += n_units) {
         const int t = item % n_tiles, sp = item / n_tiles;
         const int tmi = g.n_fast ? t / tiles_n : t % tiles_m, tni = g.n_fast ? t % tiles_n : t / tiles_m;
         const int m0 = (tmi * CTAS + (int)rank) * BM, n0 = tni * BN + (int)rank * BNL;
         const int ks0 = sp * kps, ks1 = min(k_steps, ks0 + kps);
-        for (int ks = ks0; ks < ks1; ++ks, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1u;
-          mbar_wait(empty + s, ph ^ 1u);  // slot free (first pass returns immediately)
+        for (int ks = ks0; ks < ks1; ++ks) {
+          mbar_wait(empty + s, ph);  // slot free
           const int k0 = ks * BK;
-          if (CTAS == 1) {
-            mbar_expect_tx(full + s, A_STAGE + B_STAGE);
+          const uint32_t da = sA0 + s * A_STAGE, db = sB0 + s * B_STAGE, fb = fb0 + s * 8;
+          if (g.dbg & 2) {   // profiling: no loads, the MMAs chew on whatever the slot holds
+            if (rank == 0 && lane == 0) mbar_arrive(full + s);
+          } else {
+            if (CTAS == 1) expect_tx_elect(fb, A_STAGE + B_STAGE);
+            else if (rank == 0) expect_tx_elect(full0 + s * 8, 2 * (A_STAGE + B_STAGE));  // both CTAs' bytes land on the leader's barrier
             if (g.a_mn) {  // [K][M] storage: one [BK x 64] box per 64 rows of the tile
 #pragma unroll
-              for (int j = 0; j < BM / 64; ++j) tma_load_2d(sA + s * A_STAGE + j * (BK * 128), &mapA, m0 + j * 64, k0, full + s);
+              for (int j = 0; j < BM / 64; ++j) tma_load_2d_elect<CTAS>(da + j * (BK * 128), &mapA, m0 + j * 64, k0, fb);
             } else {
-              tma_load_2d(sA + s * A_STAGE, &mapA, k0, m0, full + s);
+              tma_load_2d_elect<CTAS>(da, &mapA, k0, m0, fb);
             }
             if (g.b_mn) {
 #pragma unroll
-              for (int j = 0; j < BNL / 64; ++j) tma_load_2d(sB + s * B_STAGE + j * (BK * 128), &mapB, n0 + j * 64, k0, full + s);
+              for (int j = 0; j < BNL / 64; ++j) tma_load_2d_elect<CTAS>(db + j * (BK * 128), &mapB, n0 + j * 64, k0, fb);
             } else {
-              tma_load_2d(sB + s * B_STAGE, &mapB, k0, n0, full + s);
-            }
-          } else {
-            // both CTAs' bytes are credited to the LEADER's barrier (only the leader's MMA thread waits on it)
-            if (rank == 0) mbar_expect_tx(full + s, 2 * (A_STAGE + B_STAGE));
-            const uint32_t fb = map_to_rank(smem_u32(full + s), 0);
-            if (g.a_mn) {
-#pragma unroll
-              for (int j = 0; j < BM / 64; ++j) tma_load_2d_pair(sA + s * A_STAGE + j * (BK * 128), &mapA, m0 + j * 64, k0, fb);
-            } else {
-              tma_load_2d_pair(sA + s * A_STAGE, &mapA, k0, m0, fb);
-            }
-            if (g.b_mn) {
-#pragma unroll
-              for (int j = 0; j < BNL / 64; ++j) tma_load_2d_pair(sB + s * B_STAGE + j * (BK * 128), &mapB, n0 + j * 64, k0, fb);
-            } else {
-              tma_load_2d_pair(sB + s * B_STAGE, &mapB, k0, n0, fb);
+              tma_load_2d_elect<CTAS>(db, &mapB, k0, n0, fb);
             }
           }
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer (leader CTA only) -------------------------------
-    if (lane == 0 && rank == 0) {
+    // Warp-converged: all 32 lanes run the loop, elect.sync picks the lane that issues (tc05.cuh).  Per MMA the loop body
+    // is two 32-bit adds on the descriptors' low words — the single-lane version spent 580-760 cycles per k-step (four
+    // 128-cycle MMAs) on descriptor arithmetic and the compiler's per-instruction ELECT loops and bounded the whole kernel.
+    if (rank == 0) {
       const uint32_t IDESC = make_idesc_bf16(CTAS * BM, BN) | (g.a_mn ? 1u << 15 : 0u) | (g.b_mn ? 1u << 16 : 0u);
       const uint32_t IDESC_ONES = make_idesc_bf16(CTAS * BM, 16) | (g.a_mn ? 1u << 15 : 0u);   // B = K-major tile of ones
-      const uint64_t ones_desc = make_desc_sw128(smem_u32(sOnes));
-      uint32_t it = 0, tl = 0;
+      const uint32_t a_lo0 = desc_lo_sw128(smem_u32(sA), g.a_mn != 0, BK * 128), b_lo0 = desc_lo_sw128(smem_u32(sB), g.b_mn != 0, BK * 128);
+      const uint32_t a_step = g.a_mn ? 2048u >> 4 : 32u >> 4, b_step = g.b_mn ? 2048u >> 4 : 32u >> 4;   // one K = 16 step
+      const uint32_t ones_lo = desc_lo_sw128(smem_u32(sOnes), false, 0);
+      const uint32_t empty0 = smem_u32(empty), accfull0 = smem_u32(acc_full);
+      uint32_t s = 0, ph = 0, tl = 0, nks = 0;
+      long long p_full = 0, p_acc = 0, p_t0 = g.prof ? clock64() : 0;
       for (int item = unit; item < n_items; item += n_units, ++tl) {
         const int t = item % n_tiles, sp = item / n_tiles;
         const bool bias_tile = with_bias_grad && (g.n_fast ? t % tiles_n : t / tiles_m) == 0;
         const int ks0 = sp * kps, ks1 = min(k_steps, ks0 + kps);
         const int b = tl % ACC_BUFS;
+        long long c0 = g.prof ? clock64() : 0;
         mbar_wait(acc_empty + b, ((tl / ACC_BUFS) & 1u) ^ 1u);  // every epilogue warp of the unit drained this accumulator
         fence_after_sync();
-        for (int ks = ks0; ks < ks1; ++ks, ++it) {
-          const int s = it % STAGES;
-          mbar_wait(full + s, (it / STAGES) & 1u);
+        if (g.prof) p_acc += clock64() - c0;
+        const uint32_t d_acc = tmem + b * BN, d_bias = tmem + ACC_COLS + b * 32;
+        uint32_t acc = 0;
+        for (int ks = ks0; ks < ks1; ++ks, ++nks) {
+          if (g.prof) c0 = clock64();
+          mbar_wait(full + s, ph);
           fence_after_sync();
-          const uint32_t a0 = smem_u32(sA + s * A_STAGE), b0 = smem_u32(sB + s * B_STAGE);
+          if (g.prof) p_full += clock64() - c0;
+          const uint32_t al = a_lo0 + s * (A_STAGE >> 4), bl = b_lo0 + s * (B_STAGE >> 4);
+          if (EPI == EPI_WGRAD && bias_tile) {
 #pragma unroll
-          for (int kk = 0; kk < BK / 16; ++kk) {
-            const uint64_t adesc = g.a_mn ? make_desc_sw128_mn(a0 + kk * 2048) : make_desc_sw128(a0 + kk * 32);
-            mma_bf16_g<CTAS>(tmem + b * BN, adesc, g.b_mn ? make_desc_sw128_mn(b0 + kk * 2048) : make_desc_sw128(b0 + kk * 32),
-                             IDESC, (ks != ks0) || kk != 0);
-            if (EPI == EPI_WGRAD && bias_tile)
-              mma_bf16_g<CTAS>(tmem + ACC_COLS + b * 32, adesc, ones_desc, IDESC_ONES, (ks != ks0) || kk != 0);
+            for (int kk = 0; kk < BK / 16; ++kk) {
+              mma_bf16_elect<CTAS>(d_acc, al + kk * a_step, DESC_HI_SW128, bl + kk * b_step, DESC_HI_SW128, IDESC, acc | kk);
+              mma_bf16_elect<CTAS>(d_bias, al + kk * a_step, DESC_HI_SW128, ones_lo, DESC_HI_SW128, IDESC_ONES, acc | kk);
+            }
+          } else {
+#pragma unroll
+            for (int kk = 0; kk < BK / 16; ++kk)
+              mma_bf16_elect<CTAS>(d_acc, al + kk * a_step, DESC_HI_SW128, bl + kk * b_step, DESC_HI_SW128, IDESC, acc | kk);
           }
-          mma_commit_g<CTAS>(empty + s);  // frees the smem slot (in both CTAs) when these MMAs retire
+          acc = 1;
+          mma_commit_elect<CTAS>(empty0 + s * 8);  // frees the smem slot (in both CTAs) when these MMAs retire
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
-        mma_commit_g<CTAS>(acc_full + b);
+        mma_commit_elect<CTAS>(accfull0 + b * 8);
+      }
+      if (g.prof && lane == 0) {   // issue-loop cycles, of which waiting for operands / for a free accumulator, k-steps, start, end
+        long long *pp = g.prof + (size_t)blockIdx.x * 8;
+        const long long t1 = clock64();
+        pp[0] = t1 - p_t0; pp[1] = p_full; pp[2] = p_acc; pp[3] = nks; pp[4] = p_t0; pp[5] = t1;
       }
     }
   } else {
@@ -425,7 +464,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         if (ci + EPI_PARTS < NCH) tmem_ld32_async(taddr + (ci + EPI_PARTS) * 32, rr[(cj + 1) & 1]);
         const int c0 = ci * 32;
         const int col0 = n0 + c0;
-        if (col0 < g.N) {
+        if (col0 < g.N && !(g.dbg & 1)) {
           float v[32];
           if (EPI == EPI_FWD) {
             const float4 *b4 = reinterpret_cast<const float4 *>(sb + c0);
@@ -688,6 +727,8 @@ int dispatch(int bn, const CUtensorMap &ma, const CUtensorMap &mb, const GemmArg
 }
 
 int g_force_ctas = 0;   // tests / benchmarks: 1 or 2 forces the single-CTA or the CTA-pair kernel, 0 = heuristic
+int g_gemm_dbg = 0;     // profiling only (bits 8.. of sv_gemm_force_ctas): results are garbage when set
+long long *g_gemm_prof = nullptr;
 
 int run_gemm(int epi, const void *A, int lda, int a_t, const void *B, int ldb, int b_t, GemmArgs &g, cudaStream_t st) {
   const int M = g.M, N = g.N, K = g.K;
@@ -705,6 +746,8 @@ int run_gemm(int epi, const void *A, int lda, int a_t, const void *B, int ldb, i
   // the operand with the SMALLER footprint is the one re-read across the in-flight tiles (it stays in L2); the larger one
   // is streamed from HBM exactly once
   g.n_fast = (long long)N <= (long long)M ? 1 : 0;
+  g.dbg = g_gemm_dbg;
+  g.prof = g_gemm_prof;
   int bn = 64, ctas = 1;
   pick_tile(M, N, sms, b_t != 0, g.rowmax == 0, g_force_ctas, epi == EPI_WGRAD, &bn, &ctas);
   const int units = sms / ctas;
@@ -748,8 +791,14 @@ void set_dropout(GemmArgs &g, float p, unsigned long long seed) {
 
 }  // namespace
 
+extern "C" int sv_gemm_profile(long long *buf) {
+  g_gemm_prof = buf;
+  return SV_OK;
+}
+
 extern "C" int sv_gemm_force_ctas(int ctas) {
-  g_force_ctas = ctas;
+  g_force_ctas = ctas & 0xFF;
+  g_gemm_dbg = ctas >> 8;
   return SV_OK;
 }
 

@@ -95,6 +95,58 @@ __device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint6
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// ---- warp-converged issue ---------------------------------------------------------------------------------------------
+// The issue loop of a GEMM must not run inside `if (lane == 0)`: in a divergent region the compiler cannot keep the
+// descriptors in uniform registers and wraps every UTCHMMA in an ELECT / BRA.U.ANY loop — ~35 dependent instructions per
+// MMA, so a single thread cannot issue a 128-cycle MMA every 128 cycles (measured: 580-760 cycles per four MMAs, scripts/
+// gemm_decompose.py).  Here every lane of the converged warp executes the loop, the operands are warp-uniform, and only
+// the tcgen05 instruction itself is predicated on elect.sync (the same lane every time: commit tracks the MMAs of the
+// thread that issued them).  The descriptor is passed as its two 32-bit halves: the low word (address >> 4 | LBO << 16)
+// advances by plain 32-bit adds, the high word is constant per operand.
+template <int CTAS>
+__device__ __forceinline__ void mma_bf16_elect(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                               uint32_t idesc, uint32_t accumulate) {
+  if (CTAS == 1) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+template <int CTAS>
+__device__ __forceinline__ void mma_commit_elect(uint32_t bar_smem_addr) {
+  if (CTAS == 1) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar_smem_addr)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+        ::"r"(bar_smem_addr), "h"((uint16_t)3)
+        : "memory");
+  }
+}
+// the two halves of a SWIZZLE_128B descriptor: K-major (make_desc_sw128) or MN-major slabs `slab_bytes` apart
+__device__ __forceinline__ uint32_t desc_lo_sw128(uint32_t smem_addr, bool mn, uint32_t slab_bytes) {
+  return ((smem_addr & 0x3FFFFu) >> 4) | ((mn ? (slab_bytes >> 4) : 1u) << 16);
+}
+constexpr uint32_t DESC_HI_SW128 = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+
 // all previously issued MMAs of this thread -> arrive on `bar` when complete (implies fence::before_thread_sync)
 __device__ __forceinline__ void mma_commit(uint64_t *bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
