@@ -66,8 +66,10 @@ int sv_mma_bench(int N, int a_mn, int b_mn, int iters, int blocks, long long *cy
  * 2 = the producer skips its TMA loads. */
 int sv_gemm_force_ctas(int ctas);
 
-/* Profiling: while `buf` (device, [grid][8] int64) is non-null every GEMM launch writes, per CTA, the MMA-issuing thread's
- * {loop cycles, cycles waiting for operands, cycles waiting for a free accumulator, k-steps issued, clock at start, at end}. */
+/* Profiling: while `buf` (device, [grid][16] int64) is non-null every GEMM launch writes, per CTA, the MMA-issuing thread's
+ * {loop cycles, cycles waiting for operands, cycles waiting for a free accumulator, k-steps issued, clock at start, at end,
+ * loop nanoseconds (globaltimer)}, and from slot 8 two epilogue warps' {cycles at the bias barrier, waiting for the accumulator,
+ * in the epilogue body, tiles}. */
 int sv_gemm_profile(long long *buf);
 
 /* ---- the three GEMMs of a linear layer y = x W^T + b with their fused epilogues (same tcgen05 kernel family) ------

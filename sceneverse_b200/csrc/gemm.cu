@@ -44,6 +44,7 @@ constexpr int EPI_FWD = 0, EPI_DGRAD = 1, EPI_WGRAD = 2;
 struct GemmArgs {
   int M, N, K;
   int dbg = 0;              // profiling switches (sv_gemm_force_ctas bits 8..): 1 = epilogue skips its body, 2 = producer skips TMA
+  int tma_out = 0;          // bit 0: `out` leaves through TMA tile stores (mapO), bit 1: `out2` too (mapO2) — bf16, 16-byte aligned rows
   long long *prof = nullptr;  // profiling (sv_gemm_profile): [gridDim.x][8] cycle counters of the role threads, or null
   const float *bias;        // [N] or null (FWD)
   const void *residual;     // [M,N] same dtype as out, or null (FWD; added after activation / dropout)
@@ -176,6 +177,34 @@ __device__ __forceinline__ void store_chunk_bf16(const float (&v)[32], __nv_bflo
   }
 }
 
+// ---- TMA tile stores: a warp's 32 x 32 bf16 chunk is written to its staging buffer as [32 rows][64 B] in the
+// SWIZZLE_64B pattern (16-byte piece c of row r lives at piece c ^ ((r >> 1) & 3): conflict-free 16-byte stores with one
+// row per lane), then ONE lane hands the 2 KB box to the TMA unit, which clips rows >= M / columns >= N itself.  Replaces
+// the per-lane ld.shared + address arithmetic + predicated st.global.v4 of store_chunk_bf16: the epilogue warps were
+// latency-bound at ~300 instructions per chunk (profiles: r2 gemm decomposition). ------------------------------------------
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_chunk_bf16(const float (&v)[32], const CUtensorMap *map, int col0, int wrow0, uint8_t *stg,
+                                                     int lane) {
+  if (lane == 0) tma_store_wait_read();   // the previous box of this warp has been read out of the staging buffer
+  __syncwarp();
+  const uint32_t sw = (uint32_t)(lane >> 1) & 3u;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    *reinterpret_cast<uint4 *>(stg + lane * 64 + ((k ^ sw) << 4)) =
+        make_uint4(pack_bf16(v[8 * k], v[8 * k + 1]), pack_bf16(v[8 * k + 2], v[8 * k + 3]),
+                   pack_bf16(v[8 * k + 4], v[8 * k + 5]), pack_bf16(v[8 * k + 6], v[8 * k + 7]));
+  fence_proxy_async_smem();   // generic-proxy writes -> visible to the async proxy (every writer fences, then the warp syncs)
+  __syncwarp();
+  if (lane == 0) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(reinterpret_cast<uint64_t>(map)),
+                 "r"(col0), "r"(wrow0), "r"(smem_u32(stg))
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  }
+}
+
 // ---- CTA-pair plumbing (cta_group::2): the two CTAs of a cluster sit on the two SMs of one TPC and execute ONE MMA of
 // M = 256 rows; each CTA stages its own 128 rows of A and HALF of the B tile, so per-CTA operand traffic through
 // TMA / L2 (the ~6.3 KB/clk chip-wide limit that bounds the 128 x 256 single-CTA tile at ~1.05 PFLOP/s) drops by a third
@@ -276,7 +305,8 @@ struct GemmCfg {
 
 template <int BN, int EPI, int CTAS>
 __global__ void __launch_bounds__(NTHREADS, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GemmArgs g) {
+gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+            const __grid_constant__ CUtensorMap mapO, const __grid_constant__ CUtensorMap mapO2, const GemmArgs g) {
   extern __shared__ __align__(1024) uint8_t smem[];
   using Cfg = GemmCfg<BN, CTAS>;
   constexpr int BNL = Cfg::BNL, A_STAGE = Cfg::A_STAGE, B_STAGE = Cfg::B_STAGE, STAGES = Cfg::STAGES;
@@ -291,13 +321,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
   uint8_t *sA = smem;
   uint8_t *sB = smem + STAGES * A_STAGE;
   uint8_t *sOnes = sB + STAGES * B_STAGE;                      // [16][64] bf16 ones (2 KB), WGRAD bias-gradient operand
-  uint64_t *full = reinterpret_cast<uint64_t *>(sOnes + 2048);
+  float *stage = reinterpret_cast<float *>(sOnes + 2048);   // [EPI_WARPS][STG_BYTES] store staging (512-byte aligned: TMA store
+                                                            // boxes, SWIZZLE_64B) / row-max transpose scratch
+  uint64_t *full = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(stage) + EPI_WARPS * STG_BYTES);
   uint64_t *empty = full + STAGES;
   uint64_t *acc_full = empty + STAGES;   // [2]
   uint64_t *acc_empty = acc_full + 2;    // [2]
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
-  float *stage = reinterpret_cast<float *>(tmem_slot + 4);  // [EPI_WARPS][STG_BYTES] store staging / row-max transpose scratch
-  float *sbias = stage + EPI_WARPS * STG_BYTES / 4;             // [2][BN] bias slice of the tile, double-buffered
+  float *sbias = reinterpret_cast<float *>(tmem_slot + 4);      // [2][BN] bias slice of the tile, double-buffered
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = CTAS == 2 ? cluster_rank() : 0u;
@@ -384,6 +415,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       const uint32_t empty0 = smem_u32(empty), accfull0 = smem_u32(acc_full);
       uint32_t s = 0, ph = 0, tl = 0, nks = 0;
       long long p_full = 0, p_acc = 0, p_t0 = g.prof ? clock64() : 0;
+      unsigned long long p_ns0 = 0;
+      if (g.prof) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(p_ns0));
       for (int item = unit; item < n_items; item += n_units, ++tl) {
         const int t = item % n_tiles, sp = item / n_tiles;
         const bool bias_tile = with_bias_grad && (g.n_fast ? t % tiles_n : t / tiles_m) == 0;
@@ -419,9 +452,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         mma_commit_elect<CTAS>(accfull0 + b * 8);
       }
       if (g.prof && lane == 0) {   // issue-loop cycles, of which waiting for operands / for a free accumulator, k-steps, start, end
-        long long *pp = g.prof + (size_t)blockIdx.x * 8;
+        long long *pp = g.prof + (size_t)blockIdx.x * 16;
         const long long t1 = clock64();
-        pp[0] = t1 - p_t0; pp[1] = p_full; pp[2] = p_acc; pp[3] = nks; pp[4] = p_t0; pp[5] = t1;
+        unsigned long long ns1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns1));
+        pp[0] = t1 - p_t0; pp[1] = p_full; pp[2] = p_acc; pp[3] = nks; pp[4] = p_t0; pp[5] = t1; pp[6] = (long long)(ns1 - p_ns0);
       }
     }
   } else {
@@ -436,9 +471,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     uint8_t *stg = reinterpret_cast<uint8_t *>(stage) + (warp - 2) * STG_BYTES;
     const unsigned long long seed = (EPI != EPI_WGRAD && g.t16) ? attn::effective_seed(g.seed, g.seed_offset) : 0ull;
     uint32_t tl = 0;
+    long long e_bar = 0, e_acc = 0, e_body = 0, e_c = 0;
     for (int item = unit; item < n_items; item += n_units, ++tl) {
       const int t = item % n_tiles;
       const int b = tl % ACC_BUFS;
+      if (g.prof) e_c = clock64();
       const int tmi = g.n_fast ? t / tiles_n : t % tiles_m, tni = g.n_fast ? t % tiles_n : t / tiles_m;
       const int m0 = (tmi * CTAS + (int)rank) * BM, n0 = tni * BN;
       const int row = m0 + row_in_tile;
@@ -450,8 +487,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       }
       uint32_t rk = 0;
       if (EPI != EPI_WGRAD && g.t16) rk = attn::drop_row_key(seed, (unsigned long long)row);
+      if (g.prof) { const long long c = clock64(); e_bar += c - e_c; e_c = c; }
       mbar_wait(acc_full + b, (tl / ACC_BUFS) & 1u);
       fence_after_sync();
+      if (g.prof) { const long long c = clock64(); e_acc += c - e_c; e_c = c; }
       const uint32_t taddr = tmem + b * BN + ((uint32_t)(q * 32) << 16);
       uint32_t rr[2][32];
       if (part < NCH) tmem_ld32_async(taddr + part * 32, rr[0]);
@@ -476,8 +515,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
               v[4 * i + 2] = __uint_as_float(cur[4 * i + 2]) + bb.z;
               v[4 * i + 3] = __uint_as_float(cur[4 * i + 3]) + bb.w;
             }
-            if (g.out2 != nullptr)
-              store_chunk_bf16(v, reinterpret_cast<__nv_bfloat16 *>(g.out2), g.ldo, nullptr, g.M, g.N, row, wrow0, col0, stg, lane);
+            if (g.out2 != nullptr) {
+              if (g.tma_out & 2) tma_store_chunk_bf16(v, &mapO2, col0, wrow0, stg, lane);
+              else store_chunk_bf16(v, reinterpret_cast<__nv_bfloat16 *>(g.out2), g.ldo, nullptr, g.M, g.N, row, wrow0, col0, stg, lane);
+            }
             if (g.act == 1) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
@@ -563,6 +604,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
           } else if (g.out_f32) {
             store_chunk_f32<false>(v, reinterpret_cast<float *>(g.out), g.ldo, reinterpret_cast<const float *>(g.residual), g.M,
                                    g.N, row, wrow0, col0, stg, lane);
+          } else if (g.tma_out & 1) {
+            tma_store_chunk_bf16(v, &mapO, col0, wrow0, stg, lane);
           } else {
             store_chunk_bf16(v, reinterpret_cast<__nv_bfloat16 *>(g.out), g.ldo,
                              reinterpret_cast<const __nv_bfloat16 *>(g.residual), g.M, g.N, row, wrow0, col0, stg, lane);
@@ -576,6 +619,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         attn::tmem_wait16(r16);
         if (row < g.M) atomicAdd(g.bias_grad + row, __uint_as_float(r16[0]));
       }
+      if (g.prof) e_body += clock64() - e_c;
       // this warp has finished reading the accumulator: one arrival per warp on the LEADER's barrier
       fence_before_sync();
       __syncwarp();
@@ -583,6 +627,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         if (CTAS == 1) mbar_arrive(acc_empty + b);
         else mbar_arrive_cluster(map_to_rank(smem_u32(acc_empty + b), 0));
       }
+    }
+    if (g.tma_out && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // every box has landed before the CTA exits
+    if (g.prof && lane == 0 && q == 2 && part < 2) {
+      // epilogue warps 2 / 6 (part 0 / 1 of lane quadrant 2): cycles at the bias barrier, waiting for the accumulator, in the body
+      long long *pp = g.prof + (size_t)blockIdx.x * 16 + 8 + part * 4;
+      pp[0] = e_bar; pp[1] = e_acc; pp[2] = e_body; pp[3] = tl;
     }
   }
   fence_before_sync();
@@ -604,6 +654,20 @@ int make_map(CUtensorMap *map, const void *ptr, int rows, int K, int ld, int box
   cuuint32_t es[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, es,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? SV_OK : SV_ERR_INVALID_ARG;
+}
+
+// output [rows, cols] bf16 with leading dimension ld: box = one epilogue chunk, 32 rows x 32 columns (64-byte rows, SWIZZLE_64B)
+int make_map_out(CUtensorMap *map, const void *ptr, int rows, int cols, int ld) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return SV_ERR_CUDA;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? SV_OK : SV_ERR_INVALID_ARG;
 }
@@ -637,7 +701,8 @@ int device_sms(int *dev_out) {
 }
 
 template <int BN, int EPI, int CTAS>
-int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mb, const GemmArgs &g, cudaStream_t st) {
+int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mo, const CUtensorMap &mo2, const GemmArgs &g,
+                cudaStream_t st) {
   constexpr size_t smem = GemmCfg<BN, CTAS>::SMEM;
   auto kern = gemm_kernel<BN, EPI, CTAS>;
   static bool configured[64] = {false};
@@ -653,7 +718,7 @@ int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mb, const GemmArgs &g,
   const int max_units = sms / CTAS;
   const int grid = (units < max_units ? units : max_units) * CTAS;
   if (CTAS == 1) {
-    kern<<<grid, NTHREADS, smem, st>>>(ma, mb, g);
+    kern<<<grid, NTHREADS, smem, st>>>(ma, mb, mo, mo2, g);
   } else {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
@@ -667,7 +732,7 @@ int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mb, const GemmArgs &g,
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ma, mb, g);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ma, mb, mo, mo2, g);
     if (e != cudaSuccess) {
       sv::t_last_cuda_error = (int)e;
       cudaGetLastError();
@@ -718,11 +783,12 @@ void pick_tile(int M, int N, int sms, bool mn_b, bool allow_pair, int force_ctas
 }
 
 template <int EPI, int CTAS>
-int dispatch(int bn, const CUtensorMap &ma, const CUtensorMap &mb, const GemmArgs &g, cudaStream_t st) {
-  if (bn == 256) return launch_gemm<256, EPI, CTAS>(ma, mb, g, st);
-  if (bn == 192) return launch_gemm<192, EPI, CTAS>(ma, mb, g, st);
-  if (bn == 128) return launch_gemm<128, EPI, CTAS>(ma, mb, g, st);
-  if constexpr (CTAS == 1) return launch_gemm<64, EPI, 1>(ma, mb, g, st);
+int dispatch(int bn, const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mo, const CUtensorMap &mo2, const GemmArgs &g,
+             cudaStream_t st) {
+  if (bn == 256) return launch_gemm<256, EPI, CTAS>(ma, mb, mo, mo2, g, st);
+  if (bn == 192) return launch_gemm<192, EPI, CTAS>(ma, mb, mo, mo2, g, st);
+  if (bn == 128) return launch_gemm<128, EPI, CTAS>(ma, mb, mo, mo2, g, st);
+  if constexpr (CTAS == 1) return launch_gemm<64, EPI, 1>(ma, mb, mo, mo2, g, st);
   return SV_ERR_INVALID_ARG;
 }
 
@@ -772,14 +838,31 @@ int run_gemm(int epi, const void *A, int lda, int a_t, const void *B, int ldb, i
   if (rc) return rc;
   rc = b_t ? make_map_mn(&mb, B, N, K, ldb) : make_map(&mb, B, N, K, ldb, bn / ctas);
   if (rc) return rc;
-  if (ctas == 2) {
-    if (epi == EPI_FWD) return dispatch<EPI_FWD, 2>(bn, ma, mb, g, st);
-    if (epi == EPI_DGRAD) return dispatch<EPI_DGRAD, 2>(bn, ma, mb, g, st);
-    return dispatch<EPI_WGRAD, 2>(bn, ma, mb, g, st);
+  // bf16 outputs with 16-byte aligned rows leave through TMA tile stores (the row-max and residual epilogues keep the
+  // per-lane path: they do not store the chunk as it is)
+  CUtensorMap mo = ma, mo2 = ma;   // placeholders when unused (never dereferenced by the kernel)
+  g.tma_out = 0;
+  auto tma_ok = [&](const void *ptr) {
+    return ptr != nullptr && !g.out_f32 && (g.ldo % 8) == 0 && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0;
+  };
+  if (epi != EPI_WGRAD && g.rowmax == 0 && g.residual == nullptr && tma_ok(g.out)) {
+    rc = make_map_out(&mo, g.out, M, N, g.ldo);
+    if (rc) return rc;
+    g.tma_out |= 1;
   }
-  if (epi == EPI_FWD) return dispatch<EPI_FWD, 1>(bn, ma, mb, g, st);
-  if (epi == EPI_DGRAD) return dispatch<EPI_DGRAD, 1>(bn, ma, mb, g, st);
-  return dispatch<EPI_WGRAD, 1>(bn, ma, mb, g, st);
+  if (epi == EPI_FWD && tma_ok(g.out2)) {
+    rc = make_map_out(&mo2, g.out2, M, N, g.ldo);
+    if (rc) return rc;
+    g.tma_out |= 2;
+  }
+  if (ctas == 2) {
+    if (epi == EPI_FWD) return dispatch<EPI_FWD, 2>(bn, ma, mb, mo, mo2, g, st);
+    if (epi == EPI_DGRAD) return dispatch<EPI_DGRAD, 2>(bn, ma, mb, mo, mo2, g, st);
+    return dispatch<EPI_WGRAD, 2>(bn, ma, mb, mo, mo2, g, st);
+  }
+  if (epi == EPI_FWD) return dispatch<EPI_FWD, 1>(bn, ma, mb, mo, mo2, g, st);
+  if (epi == EPI_DGRAD) return dispatch<EPI_DGRAD, 1>(bn, ma, mb, mo, mo2, g, st);
+  return dispatch<EPI_WGRAD, 1>(bn, ma, mb, mo, mo2, g, st);
 }
 
 void set_dropout(GemmArgs &g, float p, unsigned long long seed) {

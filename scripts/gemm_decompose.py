@@ -50,7 +50,7 @@ json.dump(out, open("gpurun_out/r2_gemm_decompose.json", "w"), indent=1)
 # where the MMA-issuing thread spends its cycles (sv_gemm_profile), per shape, full kernel and loads-only / MMA-only modes
 from sceneverse_b200 import _lib
 lib = _lib.gps()
-prof = torch.zeros(148 * 8, dtype=torch.int64, device="cuda")
+prof = torch.zeros(148 * 16, dtype=torch.int64, device="cuda")
 lib.sv_gemm_profile(prof.data_ptr())
 issue = {}
 for name, (fn, flops) in cases.items():
@@ -58,12 +58,14 @@ for name, (fn, flops) in cases.items():
         for dbg, tag in ((0, "full"), (1, "no_epilogue"), (3, "mma_only")):
             native.gemm_force_ctas(c | (dbg << 8))
             prof.zero_(); fn(); torch.cuda.synchronize()
-            p = prof.view(148, 8).double()
+            p = prof.view(148, 16).double()
             act = p[:, 3] > 0
             loop, wfull, wacc, ks = (float(p[act, i].mean()) for i in range(4))
             span = float(p[act, 5].max() - p[act, 4].min())
             issue[f"{name}_ctas{c}_{tag}"] = {"ctas_issuing": int(act.sum()), "loop_cycles": loop, "wait_operands": round(wfull / loop, 3),
-                                              "wait_accumulator": round(wacc / loop, 3), "k_steps": ks, "cycles_per_k_step": round(loop / ks, 1)}
+                                              "wait_accumulator": round(wacc / loop, 3), "k_steps": ks, "cycles_per_k_step": round(loop / ks, 1),
+                                              "loop_us": round(float(p[act, 6].mean()) / 1e3, 2),
+                                              "epi_warp_cycles_per_tile": {k: round(float((p[:, 8 + i] / p[:, 11].clamp(min=1)).mean()), 0) for i, k in enumerate(("bias_barrier", "wait_accumulator", "body"))}, "sm_ghz": round(loop / float(p[act, 6].mean()), 3)}
             print(name, c, tag, issue[f"{name}_ctas{c}_{tag}"], flush=True)
 lib.sv_gemm_profile(None)
 native.gemm_force_ctas(0)
