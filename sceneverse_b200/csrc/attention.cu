@@ -96,7 +96,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
     const bool qlive = qi < a.Lq;
     const bool wlive = q0 + wq * 32 < a.Lq;  // warp-uniform: this warp owns at least one query
     // ---- S = Q K^T ---------------------------------------------------------------------------------------------------
-    if (tid == 0) {
+    if (tid < 32) {   // warp 0, converged: elect.sync picks the issuing lane (tc05.cuh: warp-converged issue)
       if (q0 == 0) mbar_wait(&bars[0], 0);
       mbar_wait(&bars[1], ph_q);
       fence_after_sync();
@@ -105,9 +105,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
         const uint32_t idesc = idesc_kk(min(256, NK - n0));
 #pragma unroll
         for (int ks = 0; ks < DH / 16; ++ks)
-          mma_bf16(tmem + n0, make_desc_sw128(aQ + ks * 32), make_desc_sw128(aK + n0 * 128 + ks * 32), idesc, ks > 0);
+          mma_bf16_e(tmem + n0, make_desc_sw128(aQ + ks * 32), make_desc_sw128(aK + n0 * 128 + ks * 32), idesc, ks > 0);
       }
-      mma_commit(&bars[2]);
+      mma_commit_e(&bars[2]);
     }
     ph_q ^= 1u;
     GateW gw;
@@ -244,14 +244,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ 
     __syncthreads();
 
     // ---- O = P V (V staged once, read MN-major); O overwrites the S columns ---------------------------------------------------
-    if (tid == 0) {
+    if (tid < 32) {
       fence_after_sync();
       const uint32_t aP = smem_u32(sP), aV = smem_u32(sV);
       const uint32_t idesc = idesc_kmn(DH);
 #pragma unroll 1
       for (int ks = 0; ks < nu; ++ks)
-        mma_bf16(tmem, make_desc(aP + ks * 4096, 2048, 128), make_desc_sw128_mn(aV + ks * 2048), idesc, ks > 0);
-      mma_commit(&bars[2]);
+        mma_bf16_e(tmem, make_desc(aP + ks * 4096, 2048, 128), make_desc_sw128_mn(aV + ks * 2048), idesc, ks > 0);
+      mma_commit_e(&bars[2]);
     }
     mbar_wait(&bars[2], ph_m);
     ph_m ^= 1u;

@@ -188,7 +188,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mR1, const __grid_constant__
       const int nb = min(64, NC - blk * 64);     // columns of this block (multiple of 16)
       const int buf = cbi & 1;
       // ---- S_blk, dP_blk ---------------------------------------------------------------------------------------------
-      if (tid == 0) {
+      if (tid < 32) {   // warp 0, converged: elect.sync picks the issuing lane (tc05.cuh: warp-converged issue)
         if (blk == 0) mbar_wait(&bars[2], ph_r);
         mbar_wait(&bars[buf], (uint32_t)(cbi >> 1) & 1u);
         fence_after_sync();
@@ -197,11 +197,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mR1, const __grid_constant__
         const uint32_t idesc = idesc_kk(nb);
 #pragma unroll
         for (int ks = 0; ks < DH / 16; ++ks)
-          mma_bf16(tmem + COL_S, make_desc_sw128(aR1 + ks * 32), make_desc_sw128(aC1 + ks * 32), idesc, ks > 0);
+          mma_bf16_e(tmem + COL_S, make_desc_sw128(aR1 + ks * 32), make_desc_sw128(aC1 + ks * 32), idesc, ks > 0);
 #pragma unroll
         for (int ks = 0; ks < DH / 16; ++ks)
-          mma_bf16(tmem + COL_DP, make_desc_sw128(aR2 + ks * 32), make_desc_sw128(aC2 + ks * 32), idesc, ks > 0);
-        mma_commit(&bars[3]);
+          mma_bf16_e(tmem + COL_DP, make_desc_sw128(aR2 + ks * 32), make_desc_sw128(aC2 + ks * 32), idesc, ks > 0);
+        mma_commit_e(&bars[3]);
       }
       mbar_wait(&bars[3], ph_m);
       ph_m ^= 1u;
@@ -349,20 +349,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap mR1, const __grid_constant__
       __syncthreads();
 
       // ---- accumulate the outputs over this block's columns (column operand read MN-major) -------------------------------
-      if (tid == 0) {
+      if (tid < 32) {
         fence_after_sync();
         const uint32_t aG1 = smem_u32(sG1), aG2 = smem_u32(sG2);
         const uint32_t aC1 = smem_u32(sC) + buf * 16384, aC2 = aC1 + 8192;
         const uint32_t idesc = idesc_kmn(DH);
 #pragma unroll 1
         for (int ks = 0; ks < (nb >> 4); ++ks) {
-          mma_bf16(tmem + COL_O1, make_desc(aG1 + ks * 4096, 2048, 128), make_desc_sw128_mn(aC1 + ks * 2048), idesc,
+          mma_bf16_e(tmem + COL_O1, make_desc(aG1 + ks * 4096, 2048, 128), make_desc_sw128_mn(aC1 + ks * 2048), idesc,
                    (blk | ks) != 0);
           if (SIDE == 1)
-            mma_bf16(tmem + COL_O2, make_desc(aG2 + ks * 4096, 2048, 128), make_desc_sw128_mn(aC2 + ks * 2048), idesc,
+            mma_bf16_e(tmem + COL_O2, make_desc(aG2 + ks * 4096, 2048, 128), make_desc_sw128_mn(aC2 + ks * 2048), idesc,
                      (blk | ks) != 0);
         }
-        if (blk == nblk - 1) mma_commit(&bars[3]);
+        if (blk == nblk - 1) mma_commit_e(&bars[3]);
       }
     }
     mbar_wait(&bars[3], ph_m);

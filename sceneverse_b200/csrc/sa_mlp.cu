@@ -154,7 +154,8 @@ __global__ void __launch_bounds__(Cfg::NTHREADS_ALL, Cfg::NCG == 2 ? 2 : 1) sa_m
   const uint32_t aW1 = smem_u32(sW1), aW2 = smem_u32(sW2), aW3 = smem_u32(sW3);
   uint32_t phase[2] = {0u, 0u};
 
-  // issue layer L (1..3) of buffer b; issuer lane only, after a_ready[b]
+  // issue layer L (1..3) of buffer b, after a_ready[b]: called by a whole converged warp, elect.sync picks the issuing lane
+  // (tc05.cuh: warp-converged issue)
   auto issue = [&](int L, int b) {
     fence_after_sync();
     const uint32_t aA = smem_u32(smem + b * Cfg::A_BYTES);
@@ -163,11 +164,11 @@ __global__ void __launch_bounds__(Cfg::NTHREADS_ALL, Cfg::NCG == 2 ? 2 : 1) sa_m
     auto step = [&](uint32_t acc, uint32_t aW, int N, int KSW, int ks, uint32_t idesc) {
       const int c0 = ks * 16;
       if (c0 < KSW) {
-        mma_bf16(acc, make_desc_sw128(aA + (c0 >> 6) * (128 * 128) + ((c0 >> 4) & 3) * 32),
+        mma_bf16_e(acc, make_desc_sw128(aA + (c0 >> 6) * (128 * 128) + ((c0 >> 4) & 3) * 32),
                  make_desc_sw128(aW + (c0 >> 6) * (N * 128) + ((c0 >> 4) & 3) * 32), idesc, ks > 0);
       } else {
         const int kt = (c0 - KSW) >> 4;
-        mma_bf16(acc, make_desc(aA + Cfg::A_TAIL_OFF + kt * 4096, 2048, 128),
+        mma_bf16_e(acc, make_desc(aA + Cfg::A_TAIL_OFF + kt * 4096, 2048, 128),
                  make_desc(aW + (KSW >> 6) * (N * 128) + kt * 2 * (N * 16), N * 16, 128), idesc, ks > 0);
       }
     };
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(Cfg::NTHREADS_ALL, Cfg::NCG == 2 ? 2 : 1) sa_m
 #pragma unroll
       for (int ks = 0; ks < Cfg::N2 / 16; ++ks) step(tb, aW3, Cfg::N3, Cfg::N2, ks, IDESC3);
     }
-    mma_commit(mbar + b);
+    mma_commit_e(mbar + b);
   };
   auto wait_mma = [&](int b) {
     mbar_wait(mbar + b, phase[b]);
@@ -197,7 +198,7 @@ __global__ void __launch_bounds__(Cfg::NTHREADS_ALL, Cfg::NCG == 2 ? 2 : 1) sa_m
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(abar + b)) : "memory");
     } else {
       __syncthreads();
-      if (tid == 0) issue(L, b);
+      if (tid < 32) issue(L, b);
     }
   };
   uint32_t aphase[2] = {0u, 0u};
@@ -215,7 +216,7 @@ __global__ void __launch_bounds__(Cfg::NTHREADS_ALL, Cfg::NCG == 2 ? 2 : 1) sa_m
     if (is_issuer) {
       // same event order as the epilogue threads' program order: (L1,b0) (L1,b1) | per pair: (L2,b0) (L2,b1) (L3,b0)
       // (L3,b1) (L1',b0) (L1',b1)
-      if ((tid & 31) == 0) {
+      {
         wait_and_issue(1, 0);
         if (1 < NS) wait_and_issue(1, 1);
         for (int s = 0; s < NS; s += 2) {

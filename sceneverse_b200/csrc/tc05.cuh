@@ -141,6 +141,18 @@ __device__ __forceinline__ void mma_commit_elect(uint32_t bar_smem_addr) {
         : "memory");
   }
 }
+// 64-bit descriptor form of the same (attention kernels): call from a converged warp, lane elect.sync picks issues
+__device__ __forceinline__ void mma_bf16_e(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit_e(uint64_t *bar) { mma_commit_elect<1>(smem_u32(bar)); }
+
 // the two halves of a SWIZZLE_128B descriptor: K-major (make_desc_sw128) or MN-major slabs `slab_bytes` apart
 __device__ __forceinline__ uint32_t desc_lo_sw128(uint32_t smem_addr, bool mn, uint32_t slab_bytes) {
   return ((smem_addr & 0x3FFFFu) >> 4) | ((mn ? (slab_bytes >> 4) : 1u) << 16);
