@@ -157,12 +157,22 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const LnArgs a) {
   }
 }
 
-// backward, part 1: ds (and dx) — one warp per row, nothing carried across rows (gamma is re-read from L1 per row)
+// backward, parts 1 + 2 in one pass over (g, s): ds (and dx) — one warp per row, gamma re-read from L1 per row — AND the
+// per-CTA partial sums of dgamma = sum_rows g * xhat, dbeta = sum_rows g (a separate column-sum kernel re-read both
+// tensors: 0.32 ms per step).
+// At most 2 CTAs per SM keep the partial-sum scratch at BWD_MAX_BLOCKS rows; lane l of every warp owns the same columns,
+// so a thread carries its 8 * MAXCH column sums in registers across its rows and the 8 warps meet once in shared memory.
 template <typename T, int MAXCH, bool DROP>
-__global__ void __launch_bounds__(256) ln_bwd_dx_kernel(const LnArgs a) {
+__global__ void __launch_bounds__(256, 2) ln_bwd_fused_kernel(const LnArgs a) {
+  extern __shared__ float wsum[];  // [8 warps][2][D]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nch = a.D >> 3;
   const float invD = 1.0f / (float)a.D;
+  float pg[MAXCH][8], pb[MAXCH][8];
+#pragma unroll
+  for (int ch = 0; ch < MAXCH; ++ch)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) pg[ch][i] = pb[ch][i] = 0.f;
   for (int row = blockIdx.x * 8 + warp; row < a.R; row += gridDim.x * 8) {
     const size_t base8 = (size_t)row * nch;
     const float mean = a.mean[row], rstd = a.rstd[row];
@@ -182,6 +192,8 @@ __global__ void __launch_bounds__(256) ln_bwd_dx_kernel(const LnArgs a) {
           gy[ch][i] = g[i] * gam[i];
           s1 += gy[ch][i];
           s2 = fmaf(gy[ch][i], xh[ch][i], s2);
+          pg[ch][i] = fmaf(g[i], xh[ch][i], pg[ch][i]);
+          pb[ch][i] += g[i];
         }
       }
     }
@@ -207,44 +219,23 @@ __global__ void __launch_bounds__(256) ln_bwd_dx_kernel(const LnArgs a) {
       }
     }
   }
-}
-
-// backward, part 2: per-CTA partial sums of dgamma = sum_rows g * xhat and dbeta = sum_rows g.  Thread (tx, ty) owns the
-// 8 columns of chunk tx and walks the rows ty, ty + 4 * gridDim.x, ...: fully coalesced, no shuffles.
-constexpr int DGB_ROWS = 4;
-template <typename T>
-__global__ void __launch_bounds__(512) ln_bwd_dgb_kernel(const LnArgs a) {
-  extern __shared__ float acc[];  // [DGB_ROWS][2][D]
-  const int tx = threadIdx.x, ty = threadIdx.y;
-  const int nch = a.D >> 3;
-  float pg[8], pb[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) pg[i] = pb[i] = 0.f;
-  if (tx < nch) {
-#pragma unroll 4
-    for (int row = blockIdx.x * DGB_ROWS + ty; row < a.R; row += gridDim.x * DGB_ROWS) {
-      const float mean = __ldg(a.mean + row), rstd = __ldg(a.rstd + row);
-      float g[8], s[8];
-      Chunk<T>::load(a.g, (size_t)row * nch + tx, g);
-      Chunk<T>::load(a.s_in, (size_t)row * nch + tx, s);
+  for (int ch = 0; ch < MAXCH; ++ch) {
+    const int c = lane + 32 * ch;
+    if (c < nch) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        pg[i] = fmaf(g[i], (s[i] - mean) * rstd, pg[i]);
-        pb[i] += g[i];
+        wsum[(warp * 2) * a.D + c * 8 + i] = pg[ch][i];
+        wsum[(warp * 2 + 1) * a.D + c * 8 + i] = pb[ch][i];
       }
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      acc[(ty * 2) * a.D + tx * 8 + i] = pg[i];
-      acc[(ty * 2 + 1) * a.D + tx * 8 + i] = pb[i];
     }
   }
   __syncthreads();
   float *out = a.partials + (size_t)blockIdx.x * 2 * a.D;
-  for (int d = ty * blockDim.x + tx; d < 2 * a.D; d += blockDim.x * DGB_ROWS) {
+  for (int d = threadIdx.x; d < 2 * a.D; d += 256) {
     float v = 0.f;
 #pragma unroll
-    for (int r = 0; r < DGB_ROWS; ++r) v += acc[r * 2 * a.D + d];
+    for (int w = 0; w < 8; ++w) v += wsum[w * 2 * a.D + d];
     out[d] = v;
   }
 }
@@ -284,19 +275,20 @@ int launch_fwd(const LnArgs &a, bool has_res, bool drop, cudaStream_t st) {
 template <typename T, int MAXCH>
 int launch_bwd(const LnArgs &a, bool drop, float *dgamma, float *dbeta, int accumulate, cudaStream_t st) {
   int grid = (a.R + 7) / 8;
-  if (grid > 148 * 8) grid = 148 * 8;
-  if (drop) ln_bwd_dx_kernel<T, MAXCH, true><<<grid, 256, 0, st>>>(a);
-  else ln_bwd_dx_kernel<T, MAXCH, false><<<grid, 256, 0, st>>>(a);
+  if (grid > BWD_MAX_BLOCKS) grid = BWD_MAX_BLOCKS;
+  const size_t smem = (size_t)8 * 2 * a.D * sizeof(float);   // <= 64 KB at D = 1024
+  static bool configured = false;
+  if (!configured) {
+    int rc = sv::cuda_status(cudaFuncSetAttribute(ln_bwd_fused_kernel<T, MAXCH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    if (!rc) rc = sv::cuda_status(cudaFuncSetAttribute(ln_bwd_fused_kernel<T, MAXCH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    if (rc) return rc;
+    configured = true;
+  }
+  if (drop) ln_bwd_fused_kernel<T, MAXCH, true><<<grid, 256, smem, st>>>(a);
+  else ln_bwd_fused_kernel<T, MAXCH, false><<<grid, 256, smem, st>>>(a);
   int rc = sv::after_launch();
   if (rc) return rc;
-  int nblk = (a.R + DGB_ROWS * 4 - 1) / (DGB_ROWS * 4);  // >= 4 rows per thread before a CTA is added
-  if (nblk > BWD_MAX_BLOCKS) nblk = BWD_MAX_BLOCKS;
-  const int nch = a.D >> 3;
-  const dim3 block((unsigned)((nch + 31) / 32 * 32), DGB_ROWS);
-  ln_bwd_dgb_kernel<T><<<nblk, block, (size_t)DGB_ROWS * 2 * a.D * sizeof(float), st>>>(a);
-  rc = sv::after_launch();
-  if (rc) return rc;
-  ln_bwd_reduce_kernel<<<(2 * a.D + 31) / 32, 256, 0, st>>>(a.partials, nblk, a.D, dgamma, dbeta, accumulate);
+  ln_bwd_reduce_kernel<<<(2 * a.D + 31) / 32, 256, 0, st>>>(a.partials, grid, a.D, dgamma, dbeta, accumulate);
   return sv::after_launch();
 }
 
