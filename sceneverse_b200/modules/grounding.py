@@ -30,12 +30,17 @@ class UnifiedSpatialCrossEncoderV2(nn.Module):
         txt_len, obj_len = txt_embeds.shape[1], obj_embeds.shape[1]
         tt = self.token_type_embeddings.weight
         key_padding = torch.cat((txt_masks, obj_masks), dim=1).logical_not()
+        # The reference splits the joint sequence after every layer, re-adds loc_layers[0](obj_locs) + tt[1] to the objects
+        # and tt[0] to the text and concatenates again (unified_encoder.py:163-172).  The re-added term is the same tensor
+        # every layer (same module, same input, no dropout inside), so it is built once as one [B, T + O, C] addend and the
+        # joint sequence stays joint: one add per layer instead of two adds, a cat and a split (and their backward copies).
+        dt = txt_embeds.dtype
+        addend = torch.cat((tt[0].to(dt).expand(txt_embeds.shape[0], txt_len, -1),
+                            (self.loc_layers[0](obj_locs) + tt[1]).to(dt)), dim=1)
+        joint = torch.cat((txt_embeds, obj_embeds.to(dt)), dim=1)
         for layer in self.unified_encoder:
-            obj_embeds = obj_embeds + self.loc_layers[0](obj_locs) + tt[1]
-            txt_embeds = txt_embeds + tt[0]
-            joint = torch.cat((txt_embeds, obj_embeds), dim=1)
-            joint, _ = layer(joint, tgt_key_padding_mask=key_padding)
-            txt_embeds, obj_embeds = torch.split(joint, [txt_len, obj_len], dim=1)
+            joint, _ = layer(joint + addend, tgt_key_padding_mask=key_padding)
+        txt_embeds, obj_embeds = torch.split(joint, [txt_len, obj_len], dim=1)
         return txt_embeds, obj_embeds
 
 
@@ -60,8 +65,9 @@ class UnifiedSpatialCrossEncoderV1(nn.Module):
                 output_hidden_states=False, **kwargs):
         pairwise_locs = calc_pairwise_locs(obj_locs[:, :, :3], obj_locs[:, :, 3:], pairwise_rel_type=self.pairwise_rel_type)
         obj_pad, txt_pad = obj_masks.logical_not(), txt_masks.logical_not()
+        loc = self.loc_layers[0](obj_locs).to(obj_embeds.dtype)   # identical every layer: computed once
         for pc_layer, lang_layer in zip(self.pc_encoder, self.lang_encoder):
-            obj_embeds = obj_embeds + self.loc_layers[0](obj_locs)
+            obj_embeds = obj_embeds + loc
             obj_out, _, _ = pc_layer(obj_embeds, txt_embeds, pairwise_locs, tgt_key_padding_mask=obj_pad,
                                      memory_key_padding_mask=txt_pad)
             txt_out, _, _ = lang_layer(txt_embeds, obj_embeds, tgt_key_padding_mask=txt_pad,
@@ -89,8 +95,9 @@ class EntitySpatialCrossEncoder(nn.Module):
                 output_hidden_states=False, **kwargs):
         pairwise_locs = calc_pairwise_locs(obj_locs[:, :, :3], obj_locs[:, :, 3:], pairwise_rel_type=self.pairwise_rel_type)
         out = obj_embeds
+        loc = self.loc_layers[0](obj_locs).to(obj_embeds.dtype)   # identical every layer: computed once
         for layer in self.layers:
-            out = out + self.loc_layers[0](obj_locs)
+            out = out + loc
             out, _, _ = layer(out, txt_embeds, pairwise_locs, tgt_key_padding_mask=obj_masks.logical_not(),
                               memory_key_padding_mask=txt_masks.logical_not())
         return txt_embeds, out

@@ -76,7 +76,10 @@ class PointOpenVocabEncoder(nn.Module):
                                                pairwise_rel_type=self.pairwise_rel_type, spatial_dist_norm=True,
                                                spatial_dim=self.spatial_dim)
             key_padding = obj_masks.logical_not()
+            # the reference re-evaluates loc_layers[0](obj_locs) before every layer; same module, same input, no
+            # dropout inside -> the same tensor each time, so it is computed once (autograd sums the per-layer uses)
+            loc = self.loc_layers[0](obj_locs).to(obj_embeds.dtype)
             for layer in self.spatial_encoder:
-                obj_embeds = obj_embeds + self.loc_layers[0](obj_locs)
+                obj_embeds = obj_embeds + loc
                 obj_embeds, _ = layer(obj_embeds, pairwise_locs, tgt_key_padding_mask=key_padding)
         return obj_embeds, obj_embeds_pre, obj_sem_cls
