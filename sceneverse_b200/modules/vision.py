@@ -78,7 +78,10 @@ class PointOpenVocabEncoder(nn.Module):
             key_padding = obj_masks.logical_not()
             # the reference re-evaluates loc_layers[0](obj_locs) before every layer; same module, same input, no
             # dropout inside -> the same tensor each time, so it is computed once (autograd sums the per-layer uses)
-            loc = self.loc_layers[0](obj_locs).to(obj_embeds.dtype)
+            loc = self.loc_layers[0](obj_locs)
+            # bf16 mode: the fp32 PointNet++ features enter the token stream in the compute dtype here, once — an fp32
+            # residual stream would be re-cast to bf16 in front of every GEMM / LayerNorm of every layer, and back
+            obj_embeds = obj_embeds.to(loc.dtype)
             for layer in self.spatial_encoder:
                 obj_embeds = obj_embeds + loc
                 obj_embeds, _ = layer(obj_embeds, pairwise_locs, tgt_key_padding_mask=key_padding)
