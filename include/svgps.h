@@ -61,7 +61,9 @@ int sv_gemm_bf16_ex(const void *A, int lda, int a_transposed, const void *B, int
 int sv_mma_bench(int N, int a_mn, int b_mn, int iters, int blocks, long long *cycles_out, void *stream);
 
 /* Kernel selection of the GEMM family (tests / benchmarks): 0 = heuristic (default), 1 = single-CTA tiles (M = 128 per MMA),
- * 2 = CTA pairs (cta_group::2, M = 256 per MMA, each CTA stages half of the B tile) wherever M > 128.
+ * 2 = CTA pairs (cta_group::2, M = 256 per MMA, each CTA stages half of the B tile) wherever M > 128, 4 = CTA pairs in
+ * clusters of two that share the B tile through TMA multicast (forward / dgrad, 256-wide tiles; an experiment: only 33 clusters
+ * of four CTAs are co-resident on a B200, so it is not selected by the heuristic).
  * Bits 8.. are profiling switches that make the RESULT GARBAGE (timing only): 1 = the epilogue skips its body,
  * 2 = the producer skips its TMA loads. */
 int sv_gemm_force_ctas(int ctas);

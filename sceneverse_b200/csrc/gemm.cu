@@ -24,6 +24,8 @@
 //   EPI_WGRAD fp32 result, split-K over the work list, `red.global.add.v4.f32` straight into the (flat) gradient buffer;
 //             the bias gradient (column sums of dL/dy) comes out of the SAME main loop: one extra N = 16 MMA per K step
 //             against a constant tile of ones, accumulated in 32 spare TMEM columns (first column-tile only)
+#include <cstdio>
+#include <cstdlib>
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -68,19 +70,9 @@ struct GemmArgs {
   float *bias_grad;         // WGRAD: [M] += row sums of A (the bias gradient), or null
 };
 
-__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
-      : "memory");
-}
-// MN-major SWIZZLE_128B operand staged as 64-column slabs [BK rows][128 B] (one TMA box each): 8-row groups 1024 B apart
+// (MN-major SWIZZLE_128B operands are staged as 64-column slabs [BK rows][128 B], one TMA box each: 8-row groups 1024 B apart
 // (stride byte offset), consecutive 64-element MN blocks one slab (BK * 128 B) apart (leading byte offset); a K step of 16
-// rows advances the start address by 2048 B.  Same descriptor family the attention kernels use for P.V / dS.K.
-__device__ __forceinline__ uint64_t make_desc_sw128_mn(uint32_t smem_addr) {
-  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)((BK * 128) >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
-         (1ull << 46) | (2ull << 61);
-}
+// rows advances the start address by 2048 B — tc05.cuh desc_lo_sw128; the attention kernels read P.V / dS.K the same way.)
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -225,15 +217,8 @@ __device__ __forceinline__ uint32_t map_to_rank(uint32_t smem_addr, uint32_t ran
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-// TMA load whose completion bytes are credited to a barrier that may live in the PEER CTA (the leader's `full` barrier)
-__device__ __forceinline__ void tma_load_2d_pair(void *dst, const CUtensorMap *map, int c0, int c1, uint32_t bar_cluster_addr) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar_cluster_addr)
-      : "memory");
-}
 // warp-converged forms (every lane executes, elect.sync picks the issuing lane): TMA tile load crediting `bar_addr` (a
-// shared::cluster address — the own CTA's barrier, or with CTA pairs the leader's) and the expect_tx arrival
+// shared::cluster address — the own CTA's barrier, or with CTA pairs the pair leader's) and the expect_tx arrival
 template <int CTAS>
 __device__ __forceinline__ void tma_load_2d_elect(uint32_t dst_smem, const CUtensorMap *map, int c0, int c1, uint32_t bar_addr) {
   if (CTAS == 1) {
@@ -250,34 +235,22 @@ __device__ __forceinline__ void tma_load_2d_elect(uint32_t dst_smem, const CUten
         : "memory");
   }
 }
+// CL = 2: one box, delivered to the same shared-memory offset of every CTA in `cta_mask`; completion is signalled on the
+// barrier at `bar_addr`'s offset in the LEADER of each destination CTA's pair (cta_group::2 barrier addressing)
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst_smem, const CUtensorMap *map, int c0, int c1, uint32_t bar_addr,
+                                               uint16_t cta_mask) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+      "@q cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%2, %3}], [%4], %5;\n\t}"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar_addr), "h"(cta_mask)
+      : "memory");
+}
 __device__ __forceinline__ void expect_tx_elect(uint32_t bar_smem_addr, uint32_t bytes) {
   asm volatile(
       "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
       "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(bar_smem_addr), "r"(bytes)
       : "memory");
-}
-template <int CTAS>
-__device__ __forceinline__ void mma_bf16_g(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  if (CTAS == 1) {
-    mma_bf16(d_tmem, a_desc, b_desc, idesc, accumulate);
-  } else {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-  }
-}
-template <int CTAS>
-__device__ __forceinline__ void mma_commit_g(uint64_t *bar) {
-  if (CTAS == 1) {
-    mma_commit(bar);
-  } else {
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(smem_u32(bar)), "h"((uint16_t)3)
-                 : "memory");
-  }
 }
 template <int CTAS, uint32_t NCOLS>
 __device__ __forceinline__ void tmem_alloc_g(uint32_t *smem_dst) {
@@ -303,7 +276,7 @@ struct GemmCfg {
   static constexpr size_t SMEM = (size_t)STAGES * (A_STAGE + B_STAGE) + 2048 + (2 * STAGES + 4) * 8 + 16 + EPI_WARPS * STG_BYTES + 2 * BN * 4;
 };
 
-template <int BN, int EPI, int CTAS>
+template <int BN, int EPI, int CTAS, int CL>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
             const __grid_constant__ CUtensorMap mapO, const __grid_constant__ CUtensorMap mapO2, const GemmArgs g) {
@@ -331,9 +304,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
   float *sbias = reinterpret_cast<float *>(tmem_slot + 4);      // [2][BN] bias slice of the tile, double-buffered
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = CTAS == 2 ? cluster_rank() : 0u;
-  const int unit = blockIdx.x / CTAS, n_units = gridDim.x / CTAS;       // a unit = one CTA, or one CTA pair
-  const int tiles_m = (g.M + CTAS * BM - 1) / (CTAS * BM), tiles_n = (g.N + BN - 1) / BN;
+  // CL = 2 (CTA pairs only): a cluster of TWO pairs works on two vertically adjacent tiles of the same column block; the
+  // B tile they share is fetched once — every CTA loads 1/CL of its pair-half and the TMA unit multicasts it to the CTA of
+  // the same rank in the other pair — so a CTA pulls 24 KB instead of 32 KB per k-step through L2.
+  static_assert(CL == 1 || CTAS == 2, "multicast clusters are built from CTA pairs");
+  const uint32_t crank = CTAS == 2 ? cluster_rank() : 0u;   // rank in the cluster (0..CTAS * CL - 1)
+  const uint32_t rank = crank & 1u;                          // rank in the pair
+  const uint32_t pair = crank >> 1;                          // pair in the cluster
+  const uint32_t leader = crank & ~1u;                       // cluster rank of this pair's leader
+  const int unit = blockIdx.x / (CTAS * CL), n_units = gridDim.x / (CTAS * CL);   // a unit = one CTA, one pair, or CL pairs
+  const int tiles_m1 = (g.M + CTAS * BM - 1) / (CTAS * BM);                       // row tiles of one CTA / pair
+  const int tiles_m = (tiles_m1 + CL - 1) / CL, tiles_n = (g.N + BN - 1) / BN;    // row tiles of a unit
   const int n_tiles = tiles_m * tiles_n;
   const int k_steps = (g.K + BK - 1) / BK;
   const int kps = (k_steps + g.splits - 1) / g.splits;   // K steps per split (host guarantees every split is non-empty)
@@ -343,7 +324,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full + s, 1);
-      mbar_init(empty + s, 1);
+      mbar_init(empty + s, CL);   // one commit per pair of the cluster
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(acc_full + b, 1);
@@ -368,15 +349,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     // coordinates and addresses stay warp-uniform (see tc05.cuh: warp-converged issue).
     {
       const uint32_t full0 = smem_u32(full), sA0 = smem_u32(sA), sB0 = smem_u32(sB);
-      const uint32_t fb0 = CTAS == 2 ? map_to_rank(full0, 0) : full0;   // the leader's barriers (CTA pairs)
+      const uint32_t fb0 = CTAS == 2 ? map_to_rank(full0, leader) : full0;   // the pair leader's barriers
+      const uint16_t bmask = (uint16_t)((1u << rank) | (1u << (rank + 2)));      // CL = 2: same rank in both pairs
       uint32_t s = 0, ph = 1;   // waiting on parity 1 of a fresh barrier returns at once: the first pass finds every slot free
       for (int item = unit; item < n_items; item += n_units) {
         const int t = item % n_tiles, sp = item / n_tiles;
         const int tmi = g.n_fast ? t / tiles_n : t % tiles_m, tni = g.n_fast ? t % tiles_n : t / tiles_m;
-        const int m0 = (tmi * CTAS + (int)rank) * BM, n0 = tni * BN + (int)rank * BNL;
+        const int m0 = ((tmi * CL + (int)pair) * CTAS + (int)rank) * BM, n0 = tni * BN + (int)rank * BNL;
         const int ks0 = sp * kps, ks1 = min(k_steps, ks0 + kps);
         for (int ks = ks0; ks < ks1; ++ks) {
-          mbar_wait(empty + s, ph);  // slot free
+          mbar_wait(empty + s, ph);  // slot free (in every CTA this CTA's loads land in)
           const int k0 = ks * BK;
           const uint32_t da = sA0 + s * A_STAGE, db = sB0 + s * B_STAGE, fb = fb0 + s * 8;
           if (g.dbg & 2) {   // profiling: no loads, the MMAs chew on whatever the slot holds
@@ -390,7 +372,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
             } else {
               tma_load_2d_elect<CTAS>(da, &mapA, k0, m0, fb);
             }
-            if (g.b_mn) {
+            if (CL == 2) {
+              // this CTA's share of the pair-half: BNL / 2 rows, multicast to the same-rank CTA of both pairs
+              constexpr int QR = BNL / 2;
+              if (g.b_mn) {
+#pragma unroll
+                for (int j = 0; j < QR / 64; ++j)
+                  tma_load_2d_mc(db + ((int)pair * (QR / 64) + j) * (BK * 128), &mapB, n0 + (int)pair * QR + j * 64, k0, fb, bmask);
+              } else {
+                tma_load_2d_mc(db + (int)pair * QR * 128, &mapB, k0, n0 + (int)pair * QR, fb, bmask);
+              }
+            } else if (g.b_mn) {
 #pragma unroll
               for (int j = 0; j < BNL / 64; ++j) tma_load_2d_elect<CTAS>(db + j * (BK * 128), &mapB, n0 + j * 64, k0, fb);
             } else {
@@ -446,10 +438,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
               mma_bf16_elect<CTAS>(d_acc, al + kk * a_step, DESC_HI_SW128, bl + kk * b_step, DESC_HI_SW128, IDESC, acc | kk);
           }
           acc = 1;
-          mma_commit_elect<CTAS>(empty0 + s * 8);  // frees the smem slot (in both CTAs) when these MMAs retire
+          mma_commit_elect<CTAS>(empty0 + s * 8, (uint16_t)((1u << (CTAS * CL)) - 1u));  // frees the slot in every CTA of the cluster
           if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
-        mma_commit_elect<CTAS>(accfull0 + b * 8);
+        mma_commit_elect<CTAS>(accfull0 + b * 8, (uint16_t)(3u << leader));   // both CTAs of THIS pair
       }
       if (g.prof && lane == 0) {   // issue-loop cycles, of which waiting for operands / for a free accumulator, k-steps, start, end
         long long *pp = g.prof + (size_t)blockIdx.x * 16;
@@ -477,7 +469,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       const int b = tl % ACC_BUFS;
       if (g.prof) e_c = clock64();
       const int tmi = g.n_fast ? t / tiles_n : t % tiles_m, tni = g.n_fast ? t % tiles_n : t / tiles_m;
-      const int m0 = (tmi * CTAS + (int)rank) * BM, n0 = tni * BN;
+      const int m0 = ((tmi * CL + (int)pair) * CTAS + (int)rank) * BM, n0 = tni * BN;
       const int row = m0 + row_in_tile;
       const int wrow0 = m0 + q * 32;  // first accumulator row of this warp
       float *sb = sbias + (tl & 1) * BN;
@@ -625,7 +617,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       __syncwarp();
       if (lane == 0) {
         if (CTAS == 1) mbar_arrive(acc_empty + b);
-        else mbar_arrive_cluster(map_to_rank(smem_u32(acc_empty + b), 0));
+        else mbar_arrive_cluster(map_to_rank(smem_u32(acc_empty + b), leader));
       }
     }
     if (g.tma_out && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // every box has landed before the CTA exits
@@ -700,11 +692,11 @@ int device_sms(int *dev_out) {
   return sms_of_dev[dev];
 }
 
-template <int BN, int EPI, int CTAS>
+template <int BN, int EPI, int CTAS, int CL = 1>
 int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mo, const CUtensorMap &mo2, const GemmArgs &g,
                 cudaStream_t st) {
   constexpr size_t smem = GemmCfg<BN, CTAS>::SMEM;
-  auto kern = gemm_kernel<BN, EPI, CTAS>;
+  auto kern = gemm_kernel<BN, EPI, CTAS, CL>;
   static bool configured[64] = {false};
   int dev = 0;
   const int sms = device_sms(&dev);
@@ -714,9 +706,36 @@ int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap 
     if (rc) return rc;
     configured[dev] = true;
   }
-  const int units = ((g.M + CTAS * BM - 1) / (CTAS * BM)) * ((g.N + BN - 1) / BN) * g.splits;
-  const int max_units = sms / CTAS;
-  const int grid = (units < max_units ? units : max_units) * CTAS;
+  const int tm1 = (g.M + CTAS * BM - 1) / (CTAS * BM);
+  const int units = ((tm1 + CL - 1) / CL) * ((g.N + BN - 1) / BN) * g.splits;
+  int max_units = sms / (CTAS * CL);
+  if (CL > 1) {
+    // a cluster's CTAs must sit in one GPC: fewer clusters of four are co-resident than sms / 4 (a persistent kernel with more
+    // clusters than fit would run the rest as a second wave)
+    static int max_clusters[64] = {0};
+    if (max_clusters[dev] == 0) {
+      cudaLaunchConfig_t q{};
+      q.gridDim = dim3(sms / (CTAS * CL) * CTAS * CL);
+      q.blockDim = dim3(NTHREADS);
+      q.dynamicSmemBytes = smem;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = CTAS * CL;
+      qa[0].val.clusterDim.y = 1;
+      qa[0].val.clusterDim.z = 1;
+      q.attrs = qa;
+      q.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kern, &q) != cudaSuccess || n < 1) {
+        cudaGetLastError();
+        n = max_units;
+      }
+      max_clusters[dev] = n;
+      if (getenv("SV_GEMM_VERBOSE")) fprintf(stderr, "[svgps] co-resident clusters of %d CTAs: %d\n", CTAS * CL, n);
+    }
+    if (max_clusters[dev] < max_units) max_units = max_clusters[dev];
+  }
+  const int grid = (units < max_units ? units : max_units) * CTAS * CL;
   if (CTAS == 1) {
     kern<<<grid, NTHREADS, smem, st>>>(ma, mb, mo, mo2, g);
   } else {
@@ -727,7 +746,7 @@ int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap 
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.x = CTAS * CL;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
@@ -783,8 +802,11 @@ void pick_tile(int M, int N, int sms, bool mn_b, bool allow_pair, int force_ctas
 }
 
 template <int EPI, int CTAS>
-int dispatch(int bn, const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mo, const CUtensorMap &mo2, const GemmArgs &g,
+int dispatch(int bn, int cl, const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mo, const CUtensorMap &mo2, const GemmArgs &g,
              cudaStream_t st) {
+  if constexpr (CTAS == 2) {
+    if (cl == 2 && bn == 256) return launch_gemm<256, EPI, 2, 2>(ma, mb, mo, mo2, g, st);
+  }
   if (bn == 256) return launch_gemm<256, EPI, CTAS>(ma, mb, mo, mo2, g, st);
   if (bn == 192) return launch_gemm<192, EPI, CTAS>(ma, mb, mo, mo2, g, st);
   if (bn == 128) return launch_gemm<128, EPI, CTAS>(ma, mb, mo, mo2, g, st);
@@ -792,7 +814,8 @@ int dispatch(int bn, const CUtensorMap &ma, const CUtensorMap &mb, const CUtenso
   return SV_ERR_INVALID_ARG;
 }
 
-int g_force_ctas = 0;   // tests / benchmarks: 1 or 2 forces the single-CTA or the CTA-pair kernel, 0 = heuristic
+int g_force_ctas = 0;   // tests / benchmarks: 1 or 2 forces the single-CTA or the CTA-pair kernel, 4 = pairs in multicast clusters
+                        // of two (256-wide tiles), 0 = heuristic
 int g_gemm_dbg = 0;     // profiling only (bits 8.. of sv_gemm_force_ctas): results are garbage when set
 long long *g_gemm_prof = nullptr;
 
@@ -815,12 +838,16 @@ int run_gemm(int epi, const void *A, int lda, int a_t, const void *B, int ldb, i
   g.dbg = g_gemm_dbg;
   g.prof = g_gemm_prof;
   int bn = 64, ctas = 1;
-  pick_tile(M, N, sms, b_t != 0, g.rowmax == 0, g_force_ctas, epi == EPI_WGRAD, &bn, &ctas);
-  const int units = sms / ctas;
+  pick_tile(M, N, sms, b_t != 0, g.rowmax == 0, g_force_ctas == 4 ? 2 : g_force_ctas, epi == EPI_WGRAD, &bn, &ctas);
+  // two pairs per cluster sharing the B tile by TMA multicast: 256-wide pair tiles with at least two row tiles
+  int cl = 1;
+  if (ctas == 2 && bn == 256 && M > 2 * BM && g_force_ctas == 4 && epi != EPI_WGRAD) cl = 2;
+  const int units = sms / (ctas * cl);
   g.splits = 1;
   if (epi == EPI_WGRAD && g.red_out) {
     // split-K: the output of a weight gradient is small (a few dozen tiles), the contraction runs over every token
-    const int tiles = ((M + ctas * BM - 1) / (ctas * BM)) * ((N + bn - 1) / bn), k_steps = (K + BK - 1) / BK;
+    const int tm1 = (M + ctas * BM - 1) / (ctas * BM);
+    const int tiles = ((tm1 + cl - 1) / cl) * ((N + bn - 1) / bn), k_steps = (K + BK - 1) / BK;
     float best_eff = 0.f;
     for (int s = 1; s <= 32 && s * 4 <= k_steps; ++s) {
       const int kps = (k_steps + s - 1) / s;
@@ -836,7 +863,7 @@ int run_gemm(int epi, const void *A, int lda, int a_t, const void *B, int ldb, i
   CUtensorMap ma, mb;
   int rc = a_t ? make_map_mn(&ma, A, M, K, lda) : make_map(&ma, A, M, K, lda, BM);
   if (rc) return rc;
-  rc = b_t ? make_map_mn(&mb, B, N, K, ldb) : make_map(&mb, B, N, K, ldb, bn / ctas);
+  rc = b_t ? make_map_mn(&mb, B, N, K, ldb) : make_map(&mb, B, N, K, ldb, bn / ctas / cl);
   if (rc) return rc;
   // bf16 outputs with 16-byte aligned rows leave through TMA tile stores (the row-max and residual epilogues keep the
   // per-lane path: they do not store the chunk as it is)
@@ -856,13 +883,13 @@ int run_gemm(int epi, const void *A, int lda, int a_t, const void *B, int ldb, i
     g.tma_out |= 2;
   }
   if (ctas == 2) {
-    if (epi == EPI_FWD) return dispatch<EPI_FWD, 2>(bn, ma, mb, mo, mo2, g, st);
-    if (epi == EPI_DGRAD) return dispatch<EPI_DGRAD, 2>(bn, ma, mb, mo, mo2, g, st);
-    return dispatch<EPI_WGRAD, 2>(bn, ma, mb, mo, mo2, g, st);
+    if (epi == EPI_FWD) return dispatch<EPI_FWD, 2>(bn, cl, ma, mb, mo, mo2, g, st);
+    if (epi == EPI_DGRAD) return dispatch<EPI_DGRAD, 2>(bn, cl, ma, mb, mo, mo2, g, st);
+    return dispatch<EPI_WGRAD, 2>(bn, cl, ma, mb, mo, mo2, g, st);
   }
-  if (epi == EPI_FWD) return dispatch<EPI_FWD, 1>(bn, ma, mb, mo, mo2, g, st);
-  if (epi == EPI_DGRAD) return dispatch<EPI_DGRAD, 1>(bn, ma, mb, mo, mo2, g, st);
-  return dispatch<EPI_WGRAD, 1>(bn, ma, mb, mo, mo2, g, st);
+  if (epi == EPI_FWD) return dispatch<EPI_FWD, 1>(bn, 1, ma, mb, mo, mo2, g, st);
+  if (epi == EPI_DGRAD) return dispatch<EPI_DGRAD, 1>(bn, 1, ma, mb, mo, mo2, g, st);
+  return dispatch<EPI_WGRAD, 1>(bn, 1, ma, mb, mo, mo2, g, st);
 }
 
 void set_dropout(GemmArgs &g, float p, unsigned long long seed) {

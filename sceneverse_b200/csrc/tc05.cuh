@@ -126,8 +126,9 @@ __device__ __forceinline__ void mma_bf16_elect(uint32_t d_tmem, uint32_t a_lo, u
         : "memory");
   }
 }
+// `cta_mask` (CTA pairs only): the cluster ranks whose barrier at this offset receive the arrival
 template <int CTAS>
-__device__ __forceinline__ void mma_commit_elect(uint32_t bar_smem_addr) {
+__device__ __forceinline__ void mma_commit_elect(uint32_t bar_smem_addr, uint16_t cta_mask = 3) {
   if (CTAS == 1) {
     asm volatile(
         "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
@@ -137,7 +138,7 @@ __device__ __forceinline__ void mma_commit_elect(uint32_t bar_smem_addr) {
     asm volatile(
         "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
         "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
-        ::"r"(bar_smem_addr), "h"((uint16_t)3)
+        ::"r"(bar_smem_addr), "h"(cta_mask)
         : "memory");
   }
 }

@@ -232,5 +232,6 @@ def embedding_bwd(grad_out, ids, dw, padding_idx=-1):
 
 
 def gemm_force_ctas(n):
-    """0 = heuristic, 1 = single-CTA tiles, 2 = CTA pairs (cta_group::2) wherever the problem has more than 128 rows."""
+    """0 = heuristic, 1 = single-CTA tiles, 2 = CTA pairs (cta_group::2) wherever the problem has more than 128 rows,
+    4 = CTA pairs in multicast clusters of two (experiment); bits 8.. are timing-only profiling switches (svgps.h)."""
     _lib.check(_lib.gps(), _lib.gps().sv_gemm_force_ctas(int(n)), "sv_gemm_force_ctas")

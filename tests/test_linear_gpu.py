@@ -16,7 +16,7 @@ def rnd(*s, seed=0, scale=0.5):
     return torch.randn(*s, device="cuda", generator=g) * scale
 
 
-@pytest.fixture(params=[0, 1, 2], ids=["auto", "cta1", "cta2"])
+@pytest.fixture(params=[0, 1, 2, 4], ids=["auto", "cta1", "cta2", "cta2x2_multicast"])
 def ctas(request):
     """Every shape runs on the single-CTA kernels, on the CTA-pair (cta_group::2) kernels and under the heuristic."""
     from sceneverse_b200 import native
