@@ -29,6 +29,16 @@ def gemm(a, w, bias=None, act=None, residual=None, out_dtype=torch.bfloat16, row
     return out
 
 
+def _mask_bytes(mask):
+    """(B, L) key-padding mask as the uint8 bytes the kernels read: a bool tensor already IS one byte of 0 / 1 per element,
+    so it is re-viewed, not copied (32 cast kernels per training step otherwise)."""
+    if mask is None:
+        return None
+    if mask.dtype == torch.bool:
+        return mask.contiguous().view(torch.uint8)
+    return (mask != 0).contiguous().view(torch.uint8)
+
+
 def attention(q, k, v, num_heads, key_padding_mask=None, spatial_w=None, spatial_heads=0, pairwise_locs=None,
               return_lse=False, dropout_p=0.0, seed=0):
     """Fused attention forward: q (B,Lq,E), k/v (B,Lk,E) bf16 (views with a contiguous last dim are fine), head dim 64.
@@ -39,7 +49,7 @@ def attention(q, k, v, num_heads, key_padding_mask=None, spatial_w=None, spatial
     assert E == num_heads * 64 and q.dtype == k.dtype == v.dtype == torch.bfloat16
     assert q.stride(2) == 1 and k.stride(2) == 1 and v.stride(2) == 1
     out = torch.empty((B, Lq, E), dtype=torch.bfloat16, device=q.device)
-    kpm = key_padding_mask.to(torch.uint8).contiguous() if key_padding_mask is not None else None
+    kpm = _mask_bytes(key_padding_mask)
     sw = locs = None
     if spatial_w is not None:
         sw = spatial_w.float().contiguous()
@@ -77,7 +87,7 @@ def attention_backward(q, k, v, out, grad_out, lse, num_heads, key_padding_mask=
         dv = torch.empty((B, Lk, E), dtype=torch.bfloat16, device=dev)
         d_rs = E
     dvec = torch.empty((B, num_heads, Lq), dtype=torch.float32, device=dev)
-    kpm = key_padding_mask.to(torch.uint8).contiguous() if key_padding_mask is not None else None
+    kpm = _mask_bytes(key_padding_mask)
     sw = locs = dsw = None
     if spatial_w is not None:
         sw, locs = spatial_w.float().contiguous(), pairwise_locs.float().contiguous()
