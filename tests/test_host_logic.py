@@ -75,3 +75,18 @@ def test_dropout_mask_restatement_statistics():
     assert a.shape == (1, 2, 64, 128) and np.array_equal(a, b) and not np.array_equal(a, c)
     assert abs(a.mean() - 0.75) < 0.02
     assert not np.array_equal(a[0, 0, 0], a[0, 0, 1])
+
+
+def test_attention_mask_bytes_is_a_view_for_bool_masks():
+    """native._mask_bytes: bool key-padding masks reach the kernels as their own bytes (no cast kernel); other dtypes keep
+    the 'non-zero = ignore' meaning."""
+    import torch
+    from sceneverse_b200 import native
+    m = torch.tensor([[True, False, True], [False, False, True]])
+    b = native._mask_bytes(m)
+    assert b.dtype == torch.uint8 and b.data_ptr() == m.data_ptr() and b.tolist() == [[1, 0, 1], [0, 0, 1]]
+    assert native._mask_bytes(None) is None
+    f = torch.tensor([[2.0, 0.0, -1.0]])
+    assert native._mask_bytes(f).tolist() == [[1, 0, 1]]
+    t = m.t()                                     # non-contiguous: made contiguous, values kept
+    assert native._mask_bytes(t).tolist() == [[1, 0], [0, 0], [1, 1]]

@@ -211,3 +211,35 @@ def test_ops_embedding_autograd_matches_torch(V, pad):
     wr = w.detach().clone().requires_grad_(True)
     F.embedding(ids, wr, pad).backward(go)
     assert rel(w.grad, wr.grad) < 1e-5
+
+
+def test_gemm_profile_counters_and_timing_switches():
+    """sv_gemm_profile: every launch writes the issuing thread's cycle counters per CTA; the k-steps it reports are the
+    work list of the launch.  The timing-only switches (bits 8.. of sv_gemm_force_ctas) must leave the kernel runnable."""
+    from sceneverse_b200 import _lib, native
+    lib = _lib.gps()
+    M, N, K = 2048, 768, 512                      # 8 x 3 pair tiles of 256 x 256, 8 k-steps each
+    x, w = rnd(M, K).bfloat16(), rnd(N, K, seed=1, scale=0.05).bfloat16()
+    b = torch.zeros(N, device="cuda")
+    prof = torch.zeros(148 * 16, dtype=torch.int64, device="cuda")
+    try:
+        native.gemm_force_ctas(2)
+        assert lib.sv_gemm_profile(prof.data_ptr()) == 0
+        want = native.linear_fwd(x, w, b).float()
+        torch.cuda.synchronize()
+        p = prof.view(148, 16)
+        assert int(p[:, 3].sum()) == (M // 256) * (N // 256) * (K // 64)      # k-steps issued over all leaders
+        act = p[:, 3] > 0
+        assert bool((p[act, 0] > 0).all()) and bool((p[act, 1] <= p[act, 0]).all())   # loop cycles; waiting is part of them
+        assert bool((p[act, 6] > 0).all())                                    # globaltimer ns of the loop
+        lib.sv_gemm_profile(None)
+        for dbg in (1, 2, 3):                     # no epilogue body / no loads / neither: garbage out, but it must finish
+            native.gemm_force_ctas(2 | (dbg << 8))
+            native.linear_fwd(x, w, b)
+            torch.cuda.synchronize()
+        native.gemm_force_ctas(2)
+        again = native.linear_fwd(x, w, b).float()
+        assert torch.equal(again, want)           # the switches leave no state behind
+    finally:
+        lib.sv_gemm_profile(None)
+        native.gemm_force_ctas(0)
