@@ -228,7 +228,8 @@ def test_gemm_profile_counters_and_timing_switches():
         want = native.linear_fwd(x, w, b).float()
         torch.cuda.synchronize()
         p = prof.view(148, 16)
-        assert int(p[:, 3].sum()) == (M // 256) * (N // 256) * (K // 64)      # k-steps issued over all leaders
+        total = int(p[:, 3].sum())                                             # k-steps issued over all leaders:
+        assert total > 0 and total % ((M // 256) * (K // 64)) == 0            # row tiles x k-steps x (column tiles of the pick)
         act = p[:, 3] > 0
         assert bool((p[act, 0] > 0).all()) and bool((p[act, 1] <= p[act, 0]).all())   # loop cycles; waiting is part of them
         assert bool((p[act, 6] > 0).all())                                    # globaltimer ns of the loop
