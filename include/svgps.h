@@ -171,6 +171,14 @@ int sv_layer_norm_bwd(const void *g, const void *s, int io_bf16, int R, int D, c
 int sv_layer_norm_bwd_acc(const void *g, const void *s, int io_bf16, int R, int D, const float *gamma, const float *mean,
                           const float *rstd, float dropout_p, unsigned long long seed, void *ds, void *dx, float *dgamma,
                           float *dbeta, int accumulate, float *scratch, void *stream);
+
+/* Row-wise L2 normalisation y = x / max(||x||_2, eps) over the last dimension and its backward
+ * dx = (g - y (y . g)) / ||x|| (rows with ||x|| < eps: g / eps) — F.normalize(x, dim=-1, p=2) of the contrastive heads
+ * (optim/loss/contra_loss.py:29-30, 59-60, 86-87 in the reference) and its autograd in one kernel per direction.
+ * x / y / g / dx: (R, D) bf16 (io_bf16 = 1) or fp32, 16-byte aligned, D % 8 == 0, 8 <= D <= 1024; norm: (R) fp32. */
+int sv_l2norm_fwd(const void *x, int io_bf16, int R, int D, float eps, void *y, float *norm, void *stream);
+int sv_l2norm_bwd(const void *g, const void *y, const float *norm, int io_bf16, int R, int D, float eps, void *dx,
+                  void *stream);
 int sv_layer_norm_scratch_floats(int D);
 
 /* Every in-kernel dropout mask (attention weights, fused LayerNorm) is a pure function of (seed, indices).  A captured

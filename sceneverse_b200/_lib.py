@@ -109,6 +109,8 @@ _GPS_SIGS = {
     "sv_dropout_seed_offset": [c_void_p],
     "sv_colsum": [c_void_p, ctypes.c_longlong, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
     "sv_colsum_scratch_floats": [c_int],
+    "sv_l2norm_fwd": [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p],
+    "sv_l2norm_bwd": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p],
     "sv_gemm_force_ctas": [c_int],
     "sv_gemm_profile": [c_void_p],
     "sv_mma_bench": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],

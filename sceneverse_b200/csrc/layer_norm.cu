@@ -260,6 +260,107 @@ __global__ void __launch_bounds__(256) ln_bwd_reduce_kernel(const float *partial
   }
 }
 
+// ---- row-wise L2 normalisation (the contrastive heads: F.normalize(x, dim=-1, p=2) of optim/loss/contra_loss.py:29-30, 59-60, 86-87
+// 60-61 and its autograd: ~9 ATen kernels per call, six calls per step) -------------------------------------------------
+//   y = x / max(||x||_2, eps)          dx = (g - y (y . g)) / ||x||   (||x|| >= eps),   g / eps   (clamped rows)
+template <typename T, int MAXCH>
+__global__ void __launch_bounds__(256) l2norm_fwd_kernel(const void *x, void *y, float *norm, int R, int D, float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nch = D >> 3;
+  for (int row = blockIdx.x * 8 + warp; row < R; row += gridDim.x * 8) {
+    const size_t base8 = (size_t)row * nch;
+    float v[MAXCH][8];
+    float ss = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < MAXCH; ++ch) {
+      const int c = lane + 32 * ch;
+      if (c < nch) {
+        Chunk<T>::load(x, base8 + c, v[ch]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ss = fmaf(v[ch][i], v[ch][i], ss);
+      }
+    }
+    const float nrm = sqrtf(warp_sum(ss));
+    const float inv = 1.0f / fmaxf(nrm, eps);
+#pragma unroll
+    for (int ch = 0; ch < MAXCH; ++ch) {
+      const int c = lane + 32 * ch;
+      if (c < nch) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[ch][i] *= inv;
+        Chunk<T>::store(y, base8 + c, v[ch]);
+      }
+    }
+    if (lane == 0) norm[row] = nrm;
+  }
+}
+template <typename T, int MAXCH>
+__global__ void __launch_bounds__(256) l2norm_bwd_kernel(const void *g, const void *y, const float *norm, void *dx, int R, int D,
+                                                        float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nch = D >> 3;
+  for (int row = blockIdx.x * 8 + warp; row < R; row += gridDim.x * 8) {
+    const size_t base8 = (size_t)row * nch;
+    const float nrm = norm[row];
+    const bool clamped = nrm < eps;
+    const float inv = 1.0f / fmaxf(nrm, eps);
+    float gg[MAXCH][8], yy[MAXCH][8];
+    float dot = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < MAXCH; ++ch) {
+      const int c = lane + 32 * ch;
+      if (c < nch) {
+        Chunk<T>::load(g, base8 + c, gg[ch]);
+        Chunk<T>::load(y, base8 + c, yy[ch]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dot = fmaf(gg[ch][i], yy[ch][i], dot);
+      }
+    }
+    dot = clamped ? 0.f : warp_sum(dot);
+#pragma unroll
+    for (int ch = 0; ch < MAXCH; ++ch) {
+      const int c = lane + 32 * ch;
+      if (c < nch) {
+        float d[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] = (gg[ch][i] - yy[ch][i] * dot) * inv;
+        Chunk<T>::store(dx, base8 + c, d);
+      }
+    }
+  }
+}
+template <typename T, int MAXCH>
+int launch_l2norm(bool bwd, const void *a, const void *b, float *norm, void *out, int R, int D, float eps, cudaStream_t st) {
+  int grid = (R + 7) / 8;
+  if (grid > 148 * 8) grid = 148 * 8;
+  if (bwd) l2norm_bwd_kernel<T, MAXCH><<<grid, 256, 0, st>>>(a, b, norm, out, R, D, eps);
+  else l2norm_fwd_kernel<T, MAXCH><<<grid, 256, 0, st>>>(a, out, norm, R, D, eps);
+  return sv::after_launch();
+}
+int run_l2norm(bool bwd, const void *a, const void *b, float *norm, void *out, int io_bf16, int R, int D, float eps, void *stream) {
+  if (R < 0 || D < 8 || (D % 8) || D > 1024 || !(eps > 0.f)) return SV_ERR_INVALID_ARG;
+  if (R == 0) return SV_OK;
+  if (!a || !norm || !out || (bwd && !b)) return SV_ERR_INVALID_ARG;
+  auto al = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (!al(a) || !al(out) || (b && !al(b))) return SV_ERR_INVALID_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int maxch = (D + 255) / 256;
+  if (io_bf16) {
+    switch (maxch) {
+      case 1: return launch_l2norm<__nv_bfloat16, 1>(bwd, a, b, norm, out, R, D, eps, st);
+      case 2: return launch_l2norm<__nv_bfloat16, 2>(bwd, a, b, norm, out, R, D, eps, st);
+      case 3: return launch_l2norm<__nv_bfloat16, 3>(bwd, a, b, norm, out, R, D, eps, st);
+      default: return launch_l2norm<__nv_bfloat16, 4>(bwd, a, b, norm, out, R, D, eps, st);
+    }
+  }
+  switch (maxch) {
+    case 1: return launch_l2norm<float, 1>(bwd, a, b, norm, out, R, D, eps, st);
+    case 2: return launch_l2norm<float, 2>(bwd, a, b, norm, out, R, D, eps, st);
+    case 3: return launch_l2norm<float, 3>(bwd, a, b, norm, out, R, D, eps, st);
+    default: return launch_l2norm<float, 4>(bwd, a, b, norm, out, R, D, eps, st);
+  }
+}
+
 constexpr int BWD_MAX_BLOCKS = 296;
 
 template <typename T, int MAXCH>
@@ -365,4 +466,13 @@ extern "C" int sv_layer_norm_bwd_acc(const void *g, const void *s, int io_bf16, 
     case 3: return launch_bwd<float, 3>(a, d, dgamma, dbeta, accumulate, st);
     default: return launch_bwd<float, 4>(a, d, dgamma, dbeta, accumulate, st);
   }
+}
+
+extern "C" int sv_l2norm_fwd(const void *x, int io_bf16, int R, int D, float eps, void *y, float *norm, void *stream) {
+  return run_l2norm(false, x, nullptr, norm, y, io_bf16, R, D, eps, stream);
+}
+
+extern "C" int sv_l2norm_bwd(const void *g, const void *y, const float *norm, int io_bf16, int R, int D, float eps, void *dx,
+                             void *stream) {
+  return run_l2norm(true, g, y, const_cast<float *>(norm), dx, io_bf16, R, D, eps, stream);
 }

@@ -57,8 +57,8 @@ class TextObjWithinBatch(nn.Module):
         self.distributed = _num_gpu(cfg) > 1
 
     def forward(self, data_dict):
-        obj_feats = F.normalize(data_dict["intra_obj_embeds"], dim=-1, p=2)
-        text_feats = F.normalize(data_dict["intra_text_embed"], dim=-1, p=2)
+        obj_feats = ops.l2_normalize(data_dict["intra_obj_embeds"])
+        text_feats = ops.l2_normalize(data_dict["intra_text_embed"])
         logits = torch.einsum("bod,bd->bo", obj_feats, text_feats)
         logits = logits.masked_fill(data_dict["obj_masks"].logical_not(), -float('inf'))
         return F.cross_entropy(logits, data_dict["tgt_object_id"].squeeze(-1))
@@ -85,8 +85,8 @@ class _SymmetricInfoNCE(nn.Module):
             # reference's gather)
             a_feats, text_feats = fused(a_feats, text_feats)
         else:
-            a_feats = F.normalize(a_feats, dim=-1, p=2)
-            text_feats = F.normalize(text_feats, dim=-1, p=2)
+            a_feats = ops.l2_normalize(a_feats)
+            text_feats = ops.l2_normalize(text_feats)
             if self.distributed:
                 a_feats, text_feats = all_gather([a_feats, text_feats])
             elif self.emulate_dist:

@@ -13,7 +13,8 @@ NATIVE = {"linear": True,               # every nn.Linear: native tcgen05 GEMM f
           "spatial_attention": True,    # MultiHeadAttentionSpatial core: native tcgen05 forward and backward
           "calc_pairwise_locs": True,
           "cross_entropy": True,        # masked-LM / grounding CE: fused native forward+gradient
-          "layer_norm": True}           # dropout + residual add + LayerNorm: one native pass per direction
+          "layer_norm": True,           # dropout + residual add + LayerNorm: one native pass per direction
+          "l2_normalize": True}         # F.normalize of the contrastive heads: one native kernel per direction
 
 
 _dropout_calls = [0]
@@ -690,6 +691,48 @@ def layer_norm(x, weight, bias, eps=1e-5, residual=None, dropout_p=0.0):
     if residual is not None:
         s = residual + s
     return F.layer_norm(s, (D,), weight, bias, eps)
+
+
+class _L2NormalizeFn(torch.autograd.Function):
+    """y = x / max(||x||_2, eps) over the last dimension (csrc/layer_norm.cu l2norm_fwd / l2norm_bwd)."""
+
+    @staticmethod
+    def forward(ctx, x, eps):
+        from . import _lib
+        lib = _lib.gps()
+        D = x.shape[-1]
+        x2 = x.reshape(-1, D).contiguous()
+        R = x2.shape[0]
+        y = torch.empty_like(x2)
+        norm = torch.empty(R, dtype=torch.float32, device=x.device)
+        st = lib.sv_l2norm_fwd(x2.data_ptr(), int(x2.dtype == torch.bfloat16), R, D, float(eps), y.data_ptr(), norm.data_ptr(),
+                               torch.cuda.current_stream(x.device).cuda_stream)
+        _lib.check(lib, st, "sv_l2norm_fwd")
+        ctx.save_for_backward(y, norm)
+        ctx.eps, ctx.shape = float(eps), x.shape
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, grad):
+        from . import _lib
+        lib = _lib.gps()
+        y, norm = ctx.saved_tensors
+        R, D = y.shape
+        g2 = grad.reshape(R, D).to(y.dtype).contiguous()
+        dx = torch.empty_like(y)
+        st = lib.sv_l2norm_bwd(g2.data_ptr(), y.data_ptr(), norm.data_ptr(), int(y.dtype == torch.bfloat16), R, D, ctx.eps,
+                               dx.data_ptr(), torch.cuda.current_stream(y.device).cuda_stream)
+        _lib.check(lib, st, "sv_l2norm_bwd")
+        return dx.view(ctx.shape), None
+
+
+def l2_normalize(x, eps=1e-12):
+    """F.normalize(x, dim=-1, p=2, eps=eps) (the contrastive heads of optim/loss/contra_loss.py:29-30,59-60,86-87).  CUDA, bf16 / fp32,
+    last dimension a multiple of 8 up to 1024: one native kernel per direction; otherwise torch."""
+    D = x.shape[-1]
+    if x.is_cuda and x.dtype in (torch.bfloat16, torch.float32) and D % 8 == 0 and 8 <= D <= 1024 and x.numel() > 0:
+        return _L2NormalizeFn.apply(x, eps)
+    return F.normalize(x, dim=-1, p=2, eps=eps)
 
 
 def cross_entropy(logits, labels, ignore_index=-100):

@@ -378,3 +378,30 @@ def test_rerouted_bert_matches_huggingface_bert_gpu():
             continue
         rel = (p.grad.float() - q.grad).abs().max().item() / (q.grad.abs().max().item() + 2e-3 * scale)
         assert rel < 8e-2, (n, rel)
+
+
+@pytest.mark.parametrize("shape,dtype", [((64, 80, 768), torch.float32), ((64, 768), torch.float32), ((37, 768), torch.bfloat16),
+                                          ((5, 3, 264), torch.float32)])
+def test_l2_normalize_matches_torch_forward_and_backward(shape, dtype):
+    """ops.l2_normalize (csrc/layer_norm.cu l2norm_*) against F.normalize(dim=-1, p=2) and its autograd, incl. an all-zero row
+    (clamped by eps: y = 0, dx = g / eps)."""
+    import torch.nn.functional as F
+    from sceneverse_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(*shape, device="cuda", generator=g).to(dtype)
+    x.view(-1, shape[-1])[1].zero_()
+    go = torch.randn(*shape, device="cuda", generator=g).to(dtype)
+    x1 = x.clone().requires_grad_()
+    y1 = ops.l2_normalize(x1)
+    y1.backward(go)
+    x2 = x.float().clone().requires_grad_()
+    y2 = F.normalize(x2, dim=-1, p=2)
+    y2.backward(go.float())
+    tol = 1e-5 if dtype == torch.float32 else 1.2e-2
+    assert y1.dtype == dtype and torch.allclose(y1.float(), y2, atol=tol, rtol=tol)
+    live = torch.ones(x.view(-1, shape[-1]).shape[0], dtype=torch.bool, device="cuda")
+    live[1] = False
+    d1, d2 = x1.grad.float().view(-1, shape[-1]), x2.grad.view(-1, shape[-1])
+    assert torch.allclose(d1[live], d2[live], atol=tol * 4, rtol=tol * 4)
+    # the clamped row: torch gives g / eps as well (the norm's own gradient at 0 is 0)
+    assert torch.allclose(d1[1], d2[1], rtol=1e-2 if dtype == torch.bfloat16 else 1e-5, atol=0)
