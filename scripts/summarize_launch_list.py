@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1] if len(sys.argv) > 1 else "r2"
 cupti = sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "gpurun_out", "r2_step_launches_cupti.json")
 ncu = sys.argv[3] if len(sys.argv) > 3 else os.path.join(ROOT, "gpurun_out", "r2_step_launches_ncu.csv")
-NATIVE = re.compile(r"(sa_sample|sa_mlp|gemm_kernel|attn_fwd|attn_bwd|fused_attn|ln_fwd|ln_bwd|colsum|pairwise_locs|ce_fwd_bwd|norm_allgather|"
+NATIVE = re.compile(r"(sa_sample|sa_mlp|gemm_kernel|attn_fwd|attn_bwd|fused_attn|ln_fwd|ln_bwd|l2norm|colsum|pairwise_locs|ce_fwd_bwd|norm_allgather|"
                     r"group_points|gather_points|ball_query|fps_|three_|adamw_|sqnorm_partial|scale_inplace|act_bwd|embedding_bwd|scene_prep|token_mask|coin_mask|mma_bench)")
 
 
